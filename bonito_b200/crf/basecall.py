@@ -1,0 +1,87 @@
+"""
+Chunked basecalling: chunk -> batch -> forward -> decode -> stitch -> format.
+
+Same generator graph and result contract as `/root/reference/bonito/crf/basecall.py:13-82`; the
+forward pass and the decoder are the sm_100a kernels behind `model(...)` and
+`bonito_b200.decode.beam_search`.  Host staging differs from the reference in one respect that does not
+change results: the fp16 cast happens into a pinned buffer and the copy is asynchronous.
+"""
+
+import numpy as np
+import torch
+
+from bonito_b200.decode import beam_search, to_str
+from bonito_b200.multiprocessing import thread_iter
+from bonito_b200.util import chunk, stitch, batchify, unbatchify
+
+
+def stitch_results(results, length, size, overlap, stride, reverse=False):
+    """Stitch per-chunk results of one read (dicts are stitched key by key)."""
+    if isinstance(results, dict):
+        return {k: stitch_results(v, length, size, overlap, stride, reverse=reverse) for k, v in results.items()}
+    if length < size:
+        return results[0, :int(np.floor(length / stride))]
+    return stitch(results, size, overlap, length, stride, reverse=reverse)
+
+
+def _stage_to_device(batch, device):
+    """fp16 cast into pinned memory + async H2D (reference: `batch.to(torch.float16).to(device)`)."""
+    if torch.device(device).type != "cuda":
+        return batch.to(torch.float16).to(device)
+    pinned = torch.empty(batch.shape, dtype=torch.float16, pin_memory=True)
+    pinned.copy_(batch)
+    return pinned.to(device, non_blocking=True)
+
+
+def compute_scores(model, batch, beam_width=32, beam_cut=100.0, scale=1.0, offset=0.0, blank_score=2.0,
+                   reverse=False):
+    """Forward + decode of one batch -> {'moves','qstring','sequence'} (CPU uint8 [N, T] each)."""
+    with torch.inference_mode():
+        device = next(model.parameters()).device
+        scores = model(_stage_to_device(batch, device))
+        if reverse:
+            # reverse_complement is defined on the blank-expanded [T, N, C] layout
+            scores = _revcomp_native(model, scores, blank_score)
+        with torch.cuda.device(scores.device):
+            sequence, qstring, moves = beam_search(
+                scores, beam_width=beam_width, beam_cut=beam_cut, scale=scale, offset=offset, blank_score=blank_score)
+        return {"moves": moves, "qstring": qstring, "sequence": sequence}
+
+
+def _revcomp_native(model, scores, blank_score):
+    """[N,T,C] (no blanks) -> reverse-complemented [N,T,C] through the reference's [T,N,C+blanks] definition."""
+    n, t, c = scores.shape
+    nb = model.seqdist.n_base
+    full = torch.nn.functional.pad(scores.permute(1, 0, 2).reshape(t, n, c // nb, nb), (1, 0), value=blank_score)
+    rc = model.seqdist.reverse_complement(full.reshape(t, n, -1)).reshape(t, n, c // nb, nb + 1)
+    return rc[..., 1:].reshape(t, n, c).permute(1, 0, 2).contiguous()
+
+
+def fmt(stride, attrs, rna=False):
+    flip = (lambda s: s[::-1]) if rna else (lambda s: s)
+    return {
+        "stride": stride,
+        "moves": attrs["moves"].numpy(),
+        "qstring": flip(to_str(attrs["qstring"])),
+        "sequence": flip(to_str(attrs["sequence"])),
+    }
+
+
+def basecall(model, reads, chunksize=4000, overlap=100, batchsize=32, reverse=False, rna=False):
+    """Basecall an iterable of reads (objects with a float32 numpy `.signal`)."""
+    qscale = float(model.config.get("qscore", {}).get("scale", 1.0)) if hasattr(model, "config") else 1.0
+    qbias = float(model.config.get("qscore", {}).get("bias", 0.0)) if hasattr(model, "config") else 0.0
+
+    chunks = thread_iter(
+        ((read, 0, read.signal.shape[-1]), chunk(torch.from_numpy(read.signal), chunksize, overlap))
+        for read in reads
+    )
+    batches = thread_iter(batchify(chunks, batchsize=batchsize))
+    scores = thread_iter(
+        (key, compute_scores(model, batch, reverse=reverse, scale=qscale, offset=qbias)) for key, batch in batches
+    )
+    results = thread_iter(
+        (read, stitch_results(out, end - start, chunksize, overlap, model.stride, reverse))
+        for ((read, start, end), out) in unbatchify(scores)
+    )
+    return thread_iter((read, fmt(model.stride, attrs, rna)) for read, attrs in results)

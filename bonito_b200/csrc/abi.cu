@@ -1,0 +1,101 @@
+// extern "C" surface of libbonito_b200.so (declared in include/bonito_b200.h).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/bonito_b200.h"
+#include "common.cuh"
+
+int launch_conv_stem(const __half* x, int N, int L, int C1, int K1, const __half* w1, const __half* b1, int act1,
+                     int C2, int K2, const __half* w2, const __half* b2, int act2, __half* out, int Lp, int padl,
+                     cudaStream_t stream);
+int lstm_rec_cluster_size(int H);
+int launch_lstm_rec(const __half* gx, const __half* whh, __half* y, int T, int N, int H, int reverse,
+                    cudaStream_t stream);
+size_t crf_decode_workspace_bytes(int N, int T, int state_len);
+int launch_crf_decode(const __half* scores, int N, int T, int state_len, float blank, float qscale, float qbias,
+                      void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream);
+
+static std::mutex g_err_mutex;
+static char g_err[1024] = "";
+
+void b200_set_error(const char* fmt, ...) {
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int b200_version(void) { return 100; }
+
+const char* b200_last_error(void) { return g_err; }
+
+int b200_conv_stem_fwd(const void* x, int n, int l, int c1, int k1, const void* w1, const void* b1, int act1,
+                       int c2, int k2, const void* w2, const void* b2, int act2, void* out, int lp, int padl,
+                       void* stream) {
+    B200_REQUIRE(x && w1 && w2 && out, "conv_stem: null pointer argument");
+    B200_REQUIRE(n >= 0 && l > 0 && lp >= padl + l, "conv_stem: bad sizes n=%d l=%d lp=%d padl=%d", n, l, lp, padl);
+    if (n == 0) return 0;
+    return launch_conv_stem((const __half*)x, n, l, c1, k1, (const __half*)w1, (const __half*)b1, act1, c2, k2,
+                            (const __half*)w2, (const __half*)b2, act2, (__half*)out, lp, padl,
+                            (cudaStream_t)stream);
+}
+
+int b200_gemm_fwd(const void* a, long long lda, const void* b, const void* bias, void* c, long long ldc, int m,
+                  int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
+                  long long stride_inner, long long stride_outer, int impl, void* stream) {
+    B200_REQUIRE(a && b && c, "gemm: null pointer argument");
+    B200_REQUIRE(m >= 0 && n > 0 && k > 0 && rows_inner > 0, "gemm: bad sizes m=%d n=%d k=%d", m, n, k);
+    B200_REQUIRE(k % 8 == 0 && lda % 8 == 0 && n % 8 == 0 && ldc % 8 == 0,
+                 "gemm: k, lda, n, ldc must be multiples of 8 (k=%d lda=%lld n=%d ldc=%lld)", k, lda, n, ldc);
+    if (m == 0) return 0;
+    GemmEpilogue ep;
+    ep.bias = (const __half*)bias;
+    ep.act = act;
+    ep.lo = lo;
+    ep.hi = hi;
+    ep.map.rows_inner = rows_inner;
+    ep.map.valid_inner = valid_inner;
+    ep.map.stride_inner = stride_inner;
+    ep.map.stride_outer = stride_outer;
+    if (impl == B200_GEMM_AUTO) {
+        const char* env = getenv("B200_GEMM_IMPL");
+        impl = (env && strcmp(env, "mma") == 0) ? B200_GEMM_MMA_SYNC : B200_GEMM_TCGEN05;
+    }
+    if (impl == B200_GEMM_MMA_SYNC)
+        return launch_gemm_mma((const __half*)a, lda, (const __half*)b, (__half*)c, ldc, m, n, k, ep,
+                               (cudaStream_t)stream);
+    return launch_gemm_tc((const __half*)a, lda, (const __half*)b, (__half*)c, ldc, m, n, k, ep,
+                          (cudaStream_t)stream);
+}
+
+int b200_lstm_cluster_size(int hidden) { return lstm_rec_cluster_size(hidden); }
+
+int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, int hidden, int reverse,
+                      void* stream) {
+    B200_REQUIRE(gx && whh && y, "lstm_rec: null pointer argument");
+    B200_REQUIRE(t >= 0 && n >= 0, "lstm_rec: bad sizes t=%d n=%d", t, n);
+    if (t == 0 || n == 0) return 0;
+    return launch_lstm_rec((const __half*)gx, (const __half*)whh, (__half*)y, t, n, hidden, reverse,
+                           (cudaStream_t)stream);
+}
+
+size_t b200_crf_decode_workspace_bytes(int n, int t, int state_len) {
+    return crf_decode_workspace_bytes(n, t, state_len);
+}
+
+int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank_score, float qscale, float qbias,
+                    void* workspace, void* moves, void* sequence, void* qstring, void* stream) {
+    B200_REQUIRE(n >= 0 && t >= 0, "crf_decode: bad sizes n=%d t=%d", n, t);
+    if (n == 0 || t == 0) return 0;
+    B200_REQUIRE(scores && workspace && moves && sequence && qstring, "crf_decode: null pointer argument");
+    return launch_crf_decode((const __half*)scores, n, t, state_len, blank_score, qscale, qbias, workspace,
+                             (uint8_t*)moves, (uint8_t*)sequence, (uint8_t*)qstring, (cudaStream_t)stream);
+}
+
+}  // extern "C"

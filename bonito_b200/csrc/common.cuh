@@ -1,0 +1,123 @@
+// Shared device/host helpers for the bonito_b200 sm_100a kernels.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+// ---------------------------------------------------------------------------
+// error plumbing: every C-ABI entry point returns 0 / negative and records a
+// message retrievable through b200_last_error().
+// ---------------------------------------------------------------------------
+void b200_set_error(const char* fmt, ...);
+
+#define B200_CHECK_CUDA(expr)                                                            \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            b200_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                           __FILE__, __LINE__);                                          \
+            return -1;                                                                   \
+        }                                                                                \
+    } while (0)
+
+#define B200_REQUIRE(cond, ...)                                                          \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            b200_set_error(__VA_ARGS__);                                                 \
+            return -2;                                                                   \
+        }                                                                                \
+    } while (0)
+
+// activation codes (B200_ACT_*) are shared with the C ABI
+#include "../../include/bonito_b200.h"
+
+// ---------------------------------------------------------------------------
+// device math with the reference's fp16 rounding points
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// tanh with ~1e-6 abs error (the SFU tanh.approx is ~5e-4, too coarse for 1e-3 parity)
+__device__ __forceinline__ float tanh_f(float x) {
+    float e = __expf(-2.0f * fabsf(x));
+    float r = (1.0f - e) / (1.0f + e);
+    return copysignf(r, x);
+}
+
+__device__ __forceinline__ float swish_f(float x) { return x * sigmoid_f(x); }
+
+// Apply an epilogue activation to a value that the reference would already have
+// rounded to fp16 (conv/linear output), then round again (elementwise op output).
+__device__ __forceinline__ float apply_act_f16(float v, int act, float lo, float hi) {
+    v = round_f16(v);
+    switch (act) {
+        case B200_ACT_SWISH: return round_f16(swish_f(v));
+        case B200_ACT_TANH: return round_f16(tanh_f(v));
+        case B200_ACT_CLAMP: return fminf(fmaxf(v, lo), hi);
+        default: return v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// small PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, bool valid) {
+    uint32_t d = smem_u32(smem_dst);
+    int bytes = valid ? 16 : 0;  // src-size 0 => zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+
+// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Row remap applied by GEMM epilogues: input row r -> (outer, inner) = divmod(r, rows_inner);
+// rows with inner >= valid_inner are dropped; output row = inner*stride_inner + outer*stride_outer.
+struct RowMap {
+    int rows_inner;
+    int valid_inner;
+    long long stride_inner;
+    long long stride_outer;
+};
+
+__device__ __forceinline__ long long map_row(const RowMap& m, int r) {
+    int outer = r / m.rows_inner;
+    int inner = r - outer * m.rows_inner;
+    if (inner >= m.valid_inner) return -1;
+    return (long long)inner * m.stride_inner + (long long)outer * m.stride_outer;
+}
+
+struct GemmEpilogue {
+    const __half* bias;  // [N] or nullptr
+    int act;             // B200_ACT_*
+    float lo, hi;        // clamp bounds
+    RowMap map;
+};
+
+// Host-side launchers (defined in the .cu files, used by abi.cu)
+int launch_gemm_mma(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
+                    const GemmEpilogue& ep, cudaStream_t stream);
+int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
+                   const GemmEpilogue& ep, cudaStream_t stream);

@@ -1,0 +1,298 @@
+// CRF decode: forward-backward posteriors followed by a Viterbi pass over the log-posteriors,
+// i.e. the in-repo decode definition of the reference
+//     SeqdistModel.decode_batch  (bonito/crf/model.py:196-199)
+//       posteriors(x.float()) + 1e-8 -> log -> CTC_CRF.viterbi (bonito/crf/model.py:98-103)
+// on the sparse 5-edge state graph of CTC_CRF (bonito/crf/model.py:37-42):
+//     in-edge e=0 of state s comes from s itself (stay, fixed blank score),
+//     in-edge e=1+j comes from state j*S/4 + s/4 (move, emits base s%4).
+// Scores arrive without the blank column, [N][T][S*4] fp16 (the layout the reference hands to
+// koi.decode.beam_search, bonito/crf/basecall.py:36-40); outputs follow that call's contract:
+// three [N][T] byte arrays (moves 0/1, base char or 0, quality char or 0).
+//
+// One CTA per chunk, one thread per state.  All recurrences run in fp32 on values re-centred on
+// state 0 every step; the accumulated shifts are carried in fp64 so the per-step posterior
+// normaliser is exact to fp32 rounding no matter how long the chunk is.
+//   pass 1 (t = T-1..0): beta'      -> workspace (fp32 [T+1][S]) + shift sums (fp64 [T+1]) + logZ
+//   pass 2 (t = 0..T-1): alpha', posteriors, per-base move mass, Viterbi scores + back-pointers
+//   pass 3: trace-back through the back-pointers (staged through shared memory in blocks)
+// Tie-breaks (the reference's are whatever argmax over koi's Max-semiring gradient gives):
+// lowest in-edge index, lowest final state.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float lse5(float a, float b, float c, float d, float e) {
+    float m = fmaxf(fmaxf(fmaxf(a, b), fmaxf(c, d)), e);
+    float s = __expf(a - m) + __expf(b - m) + __expf(c - m) + __expf(d - m) + __expf(e - m);
+    return m + __logf(s);
+}
+
+template <int S>
+struct DecodeSmem {
+    static constexpr int NW = (S + 31) / 32;
+    static constexpr int TB = 16384 / S;                 // back-pointer rows per trace-back block
+    static constexpr size_t kBuf = 0;                                  // float [2][S]
+    static constexpr size_t kVit = kBuf + 2 * S * sizeof(float);       // float [2][S]
+    static constexpr size_t kUnion = kVit + 2 * S * sizeof(float);     // float [2][4*S]  |  u8 [TB][S]
+    static constexpr size_t kPart = kUnion + 2 * 4 * S * sizeof(float);
+    static constexpr size_t kRed = kPart + 2 * NW * 4 * sizeof(float);
+    static constexpr size_t kRedI = kRed + NW * sizeof(float);
+    static constexpr size_t kOut = kRedI + NW * sizeof(int) + 16;      // u8 [3][T]
+    static size_t bytes(int T) { return kOut + 3 * (size_t)T + 16; }
+};
+
+template <int S>
+__global__ void __launch_bounds__(S)
+crf_decode_kernel(const __half* __restrict__ scores, int T, float blank, float qscale, float qbias,
+                  float* __restrict__ ws_beta, double* __restrict__ ws_bsum, uint8_t* __restrict__ ws_bp,
+                  float* __restrict__ ws_pm, uint8_t* __restrict__ moves, uint8_t* __restrict__ seq,
+                  uint8_t* __restrict__ qual) {
+    using L = DecodeSmem<S>;
+    constexpr int Q = S / 4, NW = L::NW, TB = L::TB;
+    extern __shared__ __align__(16) unsigned char sm[];
+    float (*buf)[S] = reinterpret_cast<float (*)[S]>(sm + L::kBuf);
+    float (*vit)[S] = reinterpret_cast<float (*)[S]>(sm + L::kVit);
+    float (*msh)[4 * S] = reinterpret_cast<float (*)[4 * S]>(sm + L::kUnion);
+    uint8_t (*bp_blk)[S] = reinterpret_cast<uint8_t (*)[S]>(sm + L::kUnion);
+    float (*part)[NW][4] = reinterpret_cast<float (*)[NW][4]>(sm + L::kPart);
+    float* red = reinterpret_cast<float*>(sm + L::kRed);
+    int* red_i = reinterpret_cast<int*>(sm + L::kRedI);
+    uint8_t* out_sh = sm + L::kOut;
+    __shared__ float logz_sh;
+
+    const int n = blockIdx.x;
+    const int s = threadIdx.x;
+    const int lane = s & 31, warp = s >> 5;
+    const uint2* sc = reinterpret_cast<const uint2*>(scores + (size_t)n * T * S * 4) + s;  // row stride S
+    float* beta = ws_beta + (size_t)n * (T + 1) * S;
+    double* bsum = ws_bsum + (size_t)n * (T + 1);
+    uint8_t* bp = ws_bp + (size_t)n * T * S;
+    float* pm = ws_pm + (size_t)n * T * 4;
+
+    // Scatter the 4 in-edge move scores of state s to their consumers in the backward pass:
+    // in-edge j of s leaves predecessor p = j*Q + s/4 as its b = s%4 -th out-edge -> msh[4p+b] = msh[j*S+s].
+    auto scatter = [&](float* dst, uint2 raw) {
+        const __half2 m01 = *reinterpret_cast<const __half2*>(&raw.x);
+        const __half2 m23 = *reinterpret_cast<const __half2*>(&raw.y);
+        dst[0 * S + s] = __low2float(m01);
+        dst[1 * S + s] = __high2float(m01);
+        dst[2 * S + s] = __low2float(m23);
+        dst[3 * S + s] = __high2float(m23);
+    };
+
+    // ---------------- pass 1: backward ----------------
+    {
+        buf[0][s] = 0.f;
+        beta[(size_t)T * S + s] = 0.f;
+        if (s == 0) bsum[T] = 0.0;
+        scatter(msh[(T - 1) & 1], sc[(size_t)(T - 1) * S]);
+        uint2 raw_next = (T > 1) ? sc[(size_t)(T - 2) * S] : make_uint2(0, 0);
+        double acc_shift = 0.0;
+        int cur = 0;
+        __syncthreads();
+        for (int t = T - 1; t >= 0; --t) {
+            if (t > 0) scatter(msh[(t - 1) & 1], raw_next);
+            if (t > 1) raw_next = sc[(size_t)(t - 2) * S];
+            const float b0 = buf[cur][0];
+            const float4 mv = *reinterpret_cast<const float4*>(&msh[t & 1][4 * s]);
+            const float4 bs = *reinterpret_cast<const float4*>(&buf[cur][4 * (s % Q)]);
+            const float stay = blank + buf[cur][s] - b0;
+            const float v = lse5(stay, mv.x + bs.x - b0, mv.y + bs.y - b0, mv.z + bs.z - b0, mv.w + bs.w - b0);
+            acc_shift += (double)b0;
+            buf[cur ^ 1][s] = v;
+            beta[(size_t)t * S + s] = v;
+            if (s == 0) bsum[t] = acc_shift;
+            cur ^= 1;
+            __syncthreads();
+        }
+        // logZ = bsum[0] + LSE_s beta'_0[s]
+        const float v = buf[cur][s];
+        float mx = v;
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        mx = red[0];
+        for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red[w]);
+        __syncthreads();
+        float ex = __expf(v - mx);
+        for (int o = 16; o > 0; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
+        if (lane == 0) red[warp] = ex;
+        __syncthreads();
+        if (s == 0) {
+            float tot = 0.f;
+            for (int w = 0; w < NW; ++w) tot += red[w];
+            logz_sh = mx + __logf(tot);
+        }
+        __syncthreads();
+    }
+
+    // ---------------- pass 2: forward + posteriors + Viterbi ----------------
+    {
+        const double logz = bsum[0] + (double)logz_sh;
+        const int pq = s / 4;  // predecessor along in-edge 1+j is j*Q + pq
+        buf[0][s] = 0.f;
+        vit[0][s] = 0.f;
+        double asum = 0.0;
+        __syncthreads();
+        int cur = 0;
+        uint2 mraw = sc[0];
+        float bnext = beta[(size_t)1 * S + s], bnext0 = beta[(size_t)1 * S];
+        double bs_next = bsum[1];
+        for (int t = 0; t < T; ++t) {
+            uint2 mraw_n = make_uint2(0, 0);
+            float bn_n = 0.f, bn0_n = 0.f;
+            double bsn_n = 0.0;
+            if (t + 1 < T) {  // prefetch: none of this depends on the recurrence
+                mraw_n = sc[(size_t)(t + 1) * S];
+                bn_n = beta[(size_t)(t + 2) * S + s];
+                bn0_n = beta[(size_t)(t + 2) * S];
+                bsn_n = bsum[t + 2];
+            }
+            const __half2 m01 = *reinterpret_cast<const __half2*>(&mraw.x);
+            const __half2 m23 = *reinterpret_cast<const __half2*>(&mraw.y);
+            const float ms[5] = {blank, __low2float(m01), __high2float(m01), __low2float(m23), __high2float(m23)};
+            const float a0 = buf[cur][0];
+            const float v0 = vit[cur][0];
+            float ap[5], vp[5];
+            ap[0] = buf[cur][s] - a0;
+            vp[0] = vit[cur][s] - v0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ap[1 + j] = buf[cur][j * Q + pq] - a0;
+                vp[1 + j] = vit[cur][j * Q + pq] - v0;
+            }
+            // per-step normaliser (identical in every thread)
+            const float kt = (float)((double)a0 + asum + (double)bnext0 + bs_next - logz);
+            const float bshift = bnext - bnext0 + kt;
+            float x[5], best = -INFINITY, mass = 0.f;
+            int arg = 0;
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+                x[e] = ap[e] + ms[e];
+                const float post = __expf(x[e] + bshift);
+                if (e > 0) mass += post;
+                const float cand = __logf(post + 1e-8f) + vp[e];
+                if (cand > best) { best = cand; arg = e; }
+            }
+            const float anew = lse5(x[0], x[1], x[2], x[3], x[4]);
+            asum += (double)a0;
+            buf[cur ^ 1][s] = anew;
+            vit[cur ^ 1][s] = best;
+            bp[(size_t)t * S + s] = (uint8_t)arg;
+            // move mass per emitted base (s % 4): reduce lanes of equal lane%4
+            mass += __shfl_xor_sync(0xffffffffu, mass, 4);
+            mass += __shfl_xor_sync(0xffffffffu, mass, 8);
+            mass += __shfl_xor_sync(0xffffffffu, mass, 16);
+            if (lane < 4) part[t & 1][warp][lane] = mass;
+            cur ^= 1;
+            mraw = mraw_n; bnext = bn_n; bnext0 = bn0_n; bs_next = bsn_n;
+            __syncthreads();
+            if (s < 4) {
+                float tot = 0.f;
+                for (int w = 0; w < NW; ++w) tot += part[t & 1][w][s];
+                pm[(size_t)t * 4 + s] = tot;
+            }
+        }
+        // best final state: max Viterbi score, lowest state on ties
+        float v = vit[cur][s];
+        int idx = s;
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if (lane == 0) { red[warp] = v; red_i[warp] = idx; }
+        __syncthreads();
+    }
+
+    // ---------------- pass 3: trace-back ----------------
+    {
+        uint8_t* o_mov = out_sh;
+        uint8_t* o_seq = out_sh + T;
+        uint8_t* o_q = out_sh + 2 * T;
+        int state = 0;
+        if (s == 0) {
+            float v = red[0];
+            state = red_i[0];
+            for (int w = 1; w < NW; ++w)
+                if (red[w] > v) { v = red[w]; state = red_i[w]; }
+        }
+        for (int hi = T; hi > 0; hi -= TB) {
+            const int lo = max(hi - TB, 0), rows = hi - lo;
+            __syncthreads();
+            for (int i = s; i < rows * (S / 16); i += S) {
+                const int row = i / (S / 16), c = i % (S / 16);
+                *reinterpret_cast<uint4*>(&bp_blk[row][c * 16]) =
+                    *reinterpret_cast<const uint4*>(bp + (size_t)(lo + row) * S + c * 16);
+            }
+            __syncthreads();
+            if (s == 0) {
+                for (int t = hi - 1; t >= lo; --t) {
+                    const int e = bp_blk[t - lo][state];
+                    const int base = state & 3;
+                    if (e != 0) {
+                        const float p = pm[(size_t)t * 4 + base];
+                        const float err = fmaxf(1.0f - p, 1e-4f);
+                        const float qv = -10.0f * log10f(err) * qscale + qbias;
+                        int qi = (int)rintf(qv) + 33;
+                        qi = min(max(qi, 33), 126);
+                        o_mov[t] = 1;
+                        o_seq[t] = (uint8_t)("ACGT"[base]);
+                        o_q[t] = (uint8_t)qi;
+                        state = (e - 1) * Q + (state >> 2);
+                    } else {
+                        o_mov[t] = 0; o_seq[t] = 0; o_q[t] = 0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = s; t < T; t += S) {
+            moves[(size_t)n * T + t] = o_mov[t];
+            seq[(size_t)n * T + t] = o_seq[t];
+            qual[(size_t)n * T + t] = o_q[t];
+        }
+    }
+}
+
+inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+template <int S>
+int launch_decode(const __half* scores, int N, int T, float blank, float qscale, float qbias, void* workspace,
+                  uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream) {
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    size_t off = 0;
+    float* beta = reinterpret_cast<float*>(ws + off); off += align256((size_t)N * (T + 1) * S * sizeof(float));
+    double* bsum = reinterpret_cast<double*>(ws + off); off += align256((size_t)N * (T + 1) * sizeof(double));
+    float* pm = reinterpret_cast<float*>(ws + off); off += align256((size_t)N * T * 4 * sizeof(float));
+    uint8_t* bp = ws + off;
+    const size_t dyn = DecodeSmem<S>::bytes(T);
+    auto kern = crf_decode_kernel<S>;
+    B200_REQUIRE(dyn <= 200 * 1024, "crf_decode: chunk of %d frames needs %zu B of shared memory", T, dyn);
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<N, S, dyn, stream>>>(scores, T, blank, qscale, qbias, beta, bsum, bp, pm, moves, seq, qual);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+size_t crf_decode_workspace_bytes(int N, int T, int state_len) {
+    size_t S = 1;
+    for (int i = 0; i < state_len; ++i) S *= 4;
+    return align256((size_t)N * (T + 1) * S * sizeof(float)) + align256((size_t)N * (T + 1) * sizeof(double)) +
+           align256((size_t)N * T * 4 * sizeof(float)) + align256((size_t)N * T * S);
+}
+
+int launch_crf_decode(const __half* scores, int N, int T, int state_len, float blank, float qscale, float qbias,
+                      void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream) {
+    if (N == 0 || T == 0) return 0;
+    switch (state_len) {
+        case 3: return launch_decode<64>(scores, N, T, blank, qscale, qbias, workspace, moves, seq, qual, stream);
+        case 4: return launch_decode<256>(scores, N, T, blank, qscale, qbias, workspace, moves, seq, qual, stream);
+        case 5: return launch_decode<1024>(scores, N, T, blank, qscale, qbias, workspace, moves, seq, qual, stream);
+        default:
+            b200_set_error("crf_decode: state_len %d is not supported (3, 4, 5)", state_len);
+            return -2;
+    }
+}

@@ -1,0 +1,301 @@
+// C[M,N] = epilogue(A[M,K] * B[N,K]^T) on the 5th-generation tensor cores (sm_100a).
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0     TMA producer: cp.async.bulk.tensor 2D tiles (SWIZZLE_128B) of A (128 x 64) and B (BN x 64)
+//              into a 4-stage shared-memory ring, completion on mbarriers
+//   warp 1     MMA issuer: one lane issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16),
+//              accumulating in TMEM; tcgen05.commit releases ring slots / publishes accumulators
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias -> fp16 rounding -> activation ->
+//              row-remapped 16-byte stores.  TMEM holds two accumulator stages (2 x BN columns) so the
+//              epilogue of tile i overlaps the mainloop of tile i+1 (K is only 304..384 here).
+// Used for: the strided conv of the encoder (overlapping-row view of the conv-stem output, lda < K),
+// the LSTM input projections and the LinearCRFEncoder (+Clamp) -- reference call sites
+// bonito/nn.py:226,235-241 (Conv1d), :366-370 (LSTM W_ih), :283-298 + :59-67 (Linear, Clamp).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int THREADS = 192;
+
+template <int BN>
+struct TcSmem {
+    static constexpr uint32_t kA = BM * BK * 2;         // 16 KB
+    static constexpr uint32_t kB = BN * BK * 2;         // 16 / 32 KB
+    static constexpr uint32_t kStage = kA + kB;
+    static constexpr uint32_t kBars = STAGES * kStage;  // mbarriers after the ring
+    static constexpr uint32_t kTotal = kBars + 256 + 1024;  // + alignment slack
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+            "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 64 fp16 (128 B), 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address            bits [0,14)
+    d |= (uint64_t)0 << 16;                        // leading byte offset      bits [16,30) (unused, K-major swizzled)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset       bits [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep) {
+    using S = TcSmem<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
+    const uint32_t bars = base + S::kBars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
+    const int tiles = m_blocks * n_blocks;
+    const int k_blocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a));
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b));
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot),
+                     "r"((uint32_t)(2 * BN)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + S::kBars + 8u * (2 * STAGES + 4));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int mb = tile / n_blocks, nb = tile % n_blocks;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), S::kStage);
+                    tma_load_2d(base + stage * S::kStage, &map_a, full_bar(stage), kb * BK, mb * BM);
+                    tma_load_2d(base + stage * S::kStage + S::kA, &map_b, full_bar(stage), kb * BK, nb * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=f16, both K-major, N at [17,23), M at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(base + stage * S::kStage);
+                    const uint64_t bdesc = make_smem_desc(base + stage * S::kStage + S::kA);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 B per K=16 step inside the 128-B swizzle atom (encoded >> 4)
+                        tc_mma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar(stage));  // slot free once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(acc));  // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps (TMEM lanes 32*(warp%4) .. +31) =====
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int mb = tile / n_blocks, nb = tile % n_blocks;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int gm = mb * BM + quarter * 32 + lane;
+            const long long orow = (gm < M) ? map_row(ep.map, gm) : -1;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(taddr + c0, v);
+                const int gn0 = nb * BN + c0;
+                if (orow >= 0 && gn0 < N) {
+                    __half* dst = C + orow * ldc + gn0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (gn0 + g * 8 >= N) break;  // N % 8 == 0
+                        __half2 packed[4];
+                        uint4 braw = make_uint4(0, 0, 0, 0);
+                        if (ep.bias) braw = __ldg(reinterpret_cast<const uint4*>(ep.bias + gn0 + g * 8));
+                        const __half2* bh = reinterpret_cast<const __half2*>(&braw);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            float x0 = __uint_as_float(v[g * 8 + 2 * p]) + __low2float(bh[p]);
+                            float x1 = __uint_as_float(v[g * 8 + 2 * p + 1]) + __high2float(bh[p]);
+                            packed[p] = __floats2half2_rn(apply_act_f16(x0, ep.act, ep.lo, ep.hi),
+                                                          apply_act_f16(x1, ep.act, ep.lo, ep.hi));
+                        }
+                        *reinterpret_cast<uint4*>(dst + g * 8) = *reinterpret_cast<uint4*>(packed);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base),
+                     "r"((uint32_t)(2 * BN)));
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp16 tensor [rows][cols] with row stride `ld` elements, box = box_rows x 64, 128-B swizzle.
+int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    B200_REQUIRE(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+                 rows, cols, ld);
+    return 0;
+}
+
+template <int BN>
+int launch_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
+              const GemmEpilogue& ep, cudaStream_t stream) {
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, A, M, K, lda, BM);
+    if (rc) return rc;
+    rc = make_map(&map_b, B, N, K, K, BN);
+    if (rc) return rc;
+    auto kern = gemm_tc_kernel<BN>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN>::kTotal));
+    int dev = 0, sms = 0;
+    B200_CHECK_CUDA(cudaGetDevice(&dev));
+    B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < sms ? tiles : sms;
+    kern<<<grid, THREADS, TcSmem<BN>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
+                   const GemmEpilogue& ep, cudaStream_t stream) {
+    B200_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0,
+                 "gemm_tc: operands must be 16-byte aligned");
+    if (N % 256 == 0) return launch_tc<256>(A, lda, B, C, ldc, M, N, K, ep, stream);
+    return launch_tc<128>(A, lda, B, C, ldc, M, N, K, ep, stream);
+}

@@ -1,0 +1,36 @@
+"""
+Decoder op with the call contract of `koi.decode.beam_search` / `to_str`
+(`/root/reference/bonito/crf/basecall.py:7,36-40,50-54`).
+
+koi's beam search is a closed binary with no pinned outputs, so the
+arithmetic implemented here is the reference's in-repo decode definition
+(`SeqdistModel.decode_batch`, `/root/reference/bonito/crf/model.py:196-199`): exact
+forward-backward posteriors followed by a Viterbi pass over the log-posteriors.  `beam_width`
+and `beam_cut` are accepted for signature compatibility and ignored (the search is exact).
+"""
+
+import numpy as np
+import torch
+
+from bonito_b200.engine import CrfDecoder
+
+_decoder = CrfDecoder()
+
+
+def beam_search(scores, beam_width=32, beam_cut=100.0, scale=1.0, offset=0.0, blank_score=2.0):
+    """
+    scores: CUDA fp16 [N, T, 4**(k+1)] contiguous (no blank column).
+    Returns (sequence, qstring, moves): three CPU uint8 tensors [N, T]; sequence / qstring carry an
+    ASCII character on frames that emit a base and 0 elsewhere.  `scale` / `offset` are the qscore
+    scale and bias (q = -10 log10(max(1-p, 1e-4)) * scale + offset).
+    """
+    n, t, c = scores.shape
+    state_len = int(round(np.log(c) / np.log(4))) - 1
+    moves, sequence, qstring = _decoder(scores, state_len, blank_score=blank_score, qscale=scale, qbias=offset)
+    return sequence.cpu(), qstring.cpu(), moves.cpu()
+
+
+def to_str(x, encoding="ascii"):
+    """Bytes of the non-zero entries of a uint8 tensor/array, decoded."""
+    arr = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+    return arr[arr != 0].tobytes().decode(encoding)

@@ -1,0 +1,215 @@
+"""
+Plan builder + executor for the LSTM-CRF encoder (fast / hac / LSTM-sup models).
+
+`compile_lstm_crf(encoder)` walks a `bonito_b200.nn` module tree of the shape the reference's
+configs describe (`/root/reference/bonito/models/configs/dna_r10.4.1@v4.3.toml`,
+`bonito/crf/model.py:150-162`):
+
+    Convolution(1->C1,k5) , Convolution(C1->C2,k5) , Convolution(C2->H,kW,stride s)
+    Permute([2,0,1]) , LSTM x L (alternating reverse) , LinearCRFEncoder [, Clamp]
+
+and packs the weights into the operand layouts of the sm_100a kernels (include/bonito_b200.h).
+This is the native swap-in the reference performs in `Model.use_koi`
+(`bonito/crf/model.py:240-246`, koi.lstm.update_graph); like koi it returns scores as
+`[N, T, C]` fp16 without the blank column.
+
+HBM layout per batch (hac, N=512, L=9996): stem output 164 MB channels-last with halo rows;
+two [T,N,H] activation buffers (655 MB each); one [T,N,4H] gate pre-activation buffer
+(2.6 GB); scores [N,T,1024] (1.75 GB).  Buffers are cached per input shape.
+"""
+
+import torch
+
+from bonito_b200 import native
+from bonito_b200 import nn as bnn
+
+_ACT_CODES = {None: native.ACT_NONE, "swish": native.ACT_SWISH, "tanh": native.ACT_TANH}
+
+
+class UnsupportedModel(NotImplementedError):
+    pass
+
+
+def _act_code(module):
+    if module is None:
+        return native.ACT_NONE
+    name = getattr(module, "name", None)
+    if name not in _ACT_CODES:
+        raise UnsupportedModel(f"activation {module!r} has no native kernel")
+    return _ACT_CODES[name]
+
+
+def _folded_conv(layer):
+    """(weight, bias) of a Convolution with any BatchNorm folded in (bonito/nn.py:447-454)."""
+    conv = layer.conv
+    if layer.norm is not None:
+        if not isinstance(layer.norm, bnn.BatchNorm):
+            raise UnsupportedModel(f"norm {layer.norm!r} has no native kernel")
+        conv = torch.nn.utils.fusion.fuse_conv_bn_eval(conv.eval(), layer.norm.bn.eval())
+    return conv.weight.detach(), None if conv.bias is None else conv.bias.detach()
+
+
+def _dev16(t, device):
+    return None if t is None else t.to(device=device, dtype=torch.float16).contiguous()
+
+
+class LstmCrfPlan:
+    """Packed weights + cached buffers for one LSTM-CRF encoder on one device."""
+
+    def __init__(self, encoder, device):
+        layers = list(encoder.children())
+        convs = [m for m in layers if isinstance(m, bnn.Convolution)]
+        lstms = [m for m in layers if isinstance(m, bnn.LSTM)]
+        crfs = [m for m in layers if isinstance(m, bnn.LinearCRFEncoder)]
+        clamps = [m for m in layers if isinstance(m, bnn.Clamp)]
+        others = [m for m in layers if not isinstance(
+            m, (bnn.Convolution, bnn.LSTM, bnn.LinearCRFEncoder, bnn.Clamp, bnn.Permute))]
+        if len(convs) != 3 or not lstms or len(crfs) != 1 or others or len(clamps) > 1:
+            raise UnsupportedModel("native LSTM-CRF path needs 3 convolutions, >=1 LSTM, one LinearCRFEncoder "
+                                   f"and at most one Clamp; got {[type(m).__name__ for m in layers]}")
+        self.device = torch.device(device)
+
+        # --- conv stem (conv1 + conv2) -------------------------------------------------------
+        c1, c2, c3 = convs
+        for c in (c1, c2):
+            k = c.conv.kernel_size[0]
+            if c.conv.stride[0] != 1 or c.conv.padding[0] != k // 2 or k % 2 == 0:
+                raise UnsupportedModel("conv stem layers must be stride 1 with 'same' padding")
+        if c1.conv.in_channels != 1:
+            raise UnsupportedModel("the encoder must take a single input feature")
+        w1, b1 = _folded_conv(c1)
+        w2, b2 = _folded_conv(c2)
+        self.w1, self.b1, self.act1 = _dev16(w1, device), _dev16(b1, device), _act_code(c1.activation)
+        self.w2, self.b2, self.act2 = _dev16(w2, device), _dev16(b2, device), _act_code(c2.activation)
+
+        # --- strided conv as GEMM: weight [H][C2][K3] -> [H][K3*C2], k = tap*C2 + cin -------
+        w3, b3 = _folded_conv(c3)
+        self.hidden, self.c2, self.k3 = w3.shape
+        self.s3, self.pad3 = c3.conv.stride[0], c3.conv.padding[0]
+        self.w3 = _dev16(w3.permute(0, 2, 1).reshape(self.hidden, -1), device)
+        self.b3, self.act3 = _dev16(b3, device), _act_code(c3.activation)
+        if (self.k3 * self.c2) % 8 or (self.s3 * self.c2) % 8:
+            raise UnsupportedModel("strided conv window/stride must be multiples of 8 elements")
+
+        # --- LSTM stack ------------------------------------------------------------------------
+        H = self.hidden
+        if native.lstm_cluster_size(H) == 0:
+            raise UnsupportedModel(f"LSTM hidden size {H} has no native kernel")
+        unit = torch.arange(H)
+        perm_ih = (torch.arange(4)[None, :] * H + unit[:, None]).reshape(-1)          # [unit][gate]
+        perm_hh = (torch.arange(H // 8)[:, None, None] * 8 + torch.arange(4)[None, :, None] * H
+                   + torch.arange(8)[None, None, :]).reshape(-1)                      # [unit/8][gate][unit%8]
+        self.lstm = []
+        for m in lstms:
+            r = m.rnn
+            if r.hidden_size != H or r.input_size != H or r.num_layers != 1 or r.bidirectional:
+                raise UnsupportedModel("native LSTM path needs single-layer unidirectional LSTMs of equal width")
+            bias = torch.zeros(4 * H, dtype=torch.float32)
+            if r.bias:
+                bias = r.bias_ih_l0.detach().float().cpu() + r.bias_hh_l0.detach().float().cpu()
+            self.lstm.append(dict(
+                wih=_dev16(r.weight_ih_l0.detach().cpu()[perm_ih], device),
+                bias=_dev16(bias[perm_ih], device),
+                whh=_dev16(r.weight_hh_l0.detach().cpu()[perm_hh], device),
+                reverse=bool(m.reverse),
+            ))
+
+        # --- linear CRF head (+ clamp) ---------------------------------------------------------
+        crf = crfs[0]
+        if crf.activation is not None or crf.scale is not None or crf.permute is not None:
+            raise UnsupportedModel("native LinearCRFEncoder supports activation=None, scale=None, permute=None")
+        if crf.blank_score is None:
+            raise UnsupportedModel("native decode needs a fixed blank_score")
+        self.n_base, self.state_len, self.blank_score = crf.n_base, crf.state_len, float(crf.blank_score)
+        self.wl = _dev16(crf.linear.weight.detach(), device)
+        self.bl = _dev16(None if crf.linear.bias is None else crf.linear.bias.detach(), device)
+        self.n_scores = self.wl.shape[0]
+        if clamps:
+            self.act_l, self.lo, self.hi = native.ACT_CLAMP, float(clamps[0].min), float(clamps[0].max)
+        else:
+            self.act_l, self.lo, self.hi = native.ACT_NONE, 0.0, 0.0
+        self._bufs = {}
+
+    # ------------------------------------------------------------------------------------------
+    def frames(self, L):
+        return (L + 2 * self.pad3 - self.k3) // self.s3 + 1
+
+    def _buffers(self, N, L):
+        key = (N, L)
+        if key not in self._bufs:
+            self._bufs.clear()
+            T = self.frames(L)
+            need = max(self.pad3 + L, (T - 1) * self.s3 + self.k3)
+            Tp = -(-need // self.s3)
+            Lp = Tp * self.s3
+            dev, f16 = self.device, torch.float16
+            tail = self.k3 * self.c2  # the last window of the overlapping-row view reads past row N*Tp-1
+            self._bufs[key] = dict(
+                T=T, Tp=Tp, Lp=Lp,
+                stem=torch.empty(N * Lp * self.c2 + tail, dtype=f16, device=dev),
+                ya=torch.empty(T, N, self.hidden, dtype=f16, device=dev),
+                yb=torch.empty(T, N, self.hidden, dtype=f16, device=dev),
+                gx=torch.empty(T, N, 4 * self.hidden, dtype=f16, device=dev),
+            )
+            self._bufs[key]["stem"][-tail:].zero_()
+        return self._bufs[key]
+
+    def forward(self, x, out=None, gemm_impl=native.GEMM_AUTO, return_features=False):
+        """x: [N, 1, L] (or [N, L]) fp16 CUDA -> scores [N, T, C] fp16 (no blank column)."""
+        if x.dim() == 3:
+            x = x[:, 0, :]
+        x = x.to(device=self.device, dtype=torch.float16).contiguous()
+        N, L = x.shape
+        H = self.hidden
+        b = self._buffers(N, L)
+        T, Tp, Lp = b["T"], b["Tp"], b["Lp"]
+        feats = {}
+
+        native.conv_stem(x, self.w1, self.b1, self.act1, self.w2, self.b2, self.act2, b["stem"], Lp, self.pad3)
+        if return_features:
+            feats["stem"] = b["stem"][:N * Lp * self.c2].view(N, Lp, self.c2)[:, self.pad3:self.pad3 + L].clone()
+
+        # strided conv: rows r = n*Tp + t are windows of k3*c2 elements, s3*c2 apart; out[t][n][:]
+        cur, nxt = b["ya"], b["yb"]
+        native.gemm(b["stem"], self.s3 * self.c2, self.w3, self.b3, cur, H, N * Tp, H, self.k3 * self.c2,
+                    act=self.act3, rows_inner=Tp, valid_inner=T, stride_inner=N, stride_outer=1, impl=gemm_impl)
+        if return_features:
+            feats["conv"] = cur.clone()
+
+        for i, layer in enumerate(self.lstm):
+            native.gemm(cur, H, layer["wih"], layer["bias"], b["gx"], 4 * H, T * N, 4 * H, H, impl=gemm_impl)
+            native.lstm_rec(b["gx"], layer["whh"], nxt, T, N, H, layer["reverse"])
+            cur, nxt = nxt, cur
+            if return_features:
+                feats[f"lstm{i}"] = cur.clone()
+
+        if out is None:
+            out = torch.empty(N, T, self.n_scores, dtype=torch.float16, device=self.device)
+        # rows r = t*N + n -> out[n][t][:]
+        native.gemm(cur, H, self.wl, self.bl, out, self.n_scores, T * N, self.n_scores, H,
+                    act=self.act_l, lo=self.lo, hi=self.hi,
+                    rows_inner=N, valid_inner=N, stride_inner=T, stride_outer=1, impl=gemm_impl)
+        return (out, feats) if return_features else out
+
+
+def compile_lstm_crf(encoder, device):
+    return LstmCrfPlan(encoder, device)
+
+
+class CrfDecoder:
+    """Workspace-caching wrapper around b200_crf_decode."""
+
+    def __init__(self):
+        self._ws = None
+
+    def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0):
+        n, t, c = scores.shape
+        if c != 4 ** (state_len + 1):
+            raise ValueError(f"scores width {c} does not match state_len {state_len}")
+        scores = scores.to(torch.float16).contiguous()
+        need = native.crf_decode_workspace_bytes(n, t, state_len)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != scores.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=scores.device)
+        outs = [torch.empty(n, t, dtype=torch.uint8, device=scores.device) for _ in range(3)]
+        native.crf_decode(scores, state_len, blank_score, qscale, qbias, self._ws, *outs)
+        return tuple(outs)  # moves, sequence, qstring

@@ -1,0 +1,144 @@
+"""
+ctypes binding of `libbonito_b200.so` (C ABI: include/bonito_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C bonito_b200/csrc`.
+There is no CPU fallback: if the library (or a CUDA device) is missing, the native
+path raises -- see `require()`.
+"""
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbonito_b200.so")
+_lib = None
+
+ACT_NONE, ACT_SWISH, ACT_TANH, ACT_CLAMP = 0, 1, 2, 3
+GEMM_AUTO, GEMM_TCGEN05, GEMM_MMA_SYNC = 0, 1, 2
+
+# name -> (restype, argtypes); must list every symbol declared in include/bonito_b200.h
+SIGNATURES = {
+    "b200_version": (c_int, []),
+    "b200_last_error": (c_char_p, []),
+    "b200_conv_stem_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                   c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "b200_gemm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                              c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_void_p]),
+    "b200_lstm_cluster_size": (c_int, [c_int]),
+    "b200_lstm_rec_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "b200_crf_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (no CUDA calls are made by loading it)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise NativeError(
+                f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C bonito_b200/csrc` (there is no CPU fallback for the native path)")
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = lib
+    return _lib
+
+
+def require(device=None):
+    """Library + CUDA device, or a loud failure."""
+    lib = load()
+    if not torch.cuda.is_available():
+        raise NativeError("bonito_b200 native path needs a CUDA device (sm_100a); none is visible")
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load().b200_last_error().decode(errors="replace")
+        raise NativeError(f"{what} failed ({rc}): {msg}")
+
+
+def _ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f16(t, name):
+    if t.dtype != torch.float16 or not t.is_cuda or not t.is_contiguous():
+        raise NativeError(f"{name}: expected a contiguous CUDA fp16 tensor, got {t.dtype} {t.device}")
+    return t
+
+
+def version():
+    return load().b200_version()
+
+
+def conv_stem(x, w1, b1, act1, w2, b2, act2, out, lp, padl):
+    """x [N,L] -> out [N,lp,C2] channels-last, zero padded (see b200_conv_stem_fwd)."""
+    lib = require()
+    n, l = x.shape
+    c1, _, k1 = w1.shape
+    c2, _, k2 = w2.shape
+    with torch.cuda.device(x.device):
+        rc = lib.b200_conv_stem_fwd(_ptr(_f16(x, "x")), n, l, c1, k1, _ptr(_f16(w1, "w1")), _ptr(b1), act1,
+                                    c2, k2, _ptr(_f16(w2, "w2")), _ptr(b2), act2, _ptr(out), lp, padl, _stream())
+    _check(rc, "b200_conv_stem_fwd")
+    return out
+
+
+def gemm(a_ptr_tensor, lda, b, bias, c, ldc, m, n, k, act=ACT_NONE, lo=0.0, hi=0.0,
+         rows_inner=None, valid_inner=None, stride_inner=1, stride_outer=0, impl=GEMM_AUTO):
+    """C = act(A B^T + bias); `a_ptr_tensor` only supplies the base pointer (rows may overlap)."""
+    lib = require()
+    if rows_inner is None:
+        rows_inner, valid_inner = m, m
+    with torch.cuda.device(c.device):
+        rc = lib.b200_gemm_fwd(_ptr(a_ptr_tensor), lda, _ptr(_f16(b, "b")), _ptr(bias), _ptr(c), ldc, m, n, k,
+                               act, float(lo), float(hi), rows_inner, valid_inner, stride_inner, stride_outer,
+                               impl, _stream())
+    _check(rc, "b200_gemm_fwd")
+    return c
+
+
+def lstm_cluster_size(hidden):
+    return load().b200_lstm_cluster_size(hidden)
+
+
+def lstm_rec(gx, whh, y, t, n, hidden, reverse):
+    lib = require()
+    with torch.cuda.device(y.device):
+        rc = lib.b200_lstm_rec_fwd(_ptr(_f16(gx, "gx")), _ptr(_f16(whh, "whh")), _ptr(y), t, n, hidden,
+                                   int(bool(reverse)), _stream())
+    _check(rc, "b200_lstm_rec_fwd")
+    return y
+
+
+def crf_decode_workspace_bytes(n, t, state_len):
+    return load().b200_crf_decode_workspace_bytes(n, t, state_len)
+
+
+def crf_decode(scores, state_len, blank_score, qscale, qbias, workspace, moves, sequence, qstring):
+    lib = require()
+    n, t, _ = scores.shape
+    with torch.cuda.device(scores.device):
+        rc = lib.b200_crf_decode(_ptr(_f16(scores, "scores")), n, t, state_len, float(blank_score), float(qscale),
+                                 float(qbias), _ptr(workspace), _ptr(moves), _ptr(sequence), _ptr(qstring), _stream())
+    _check(rc, "b200_crf_decode")
+    return moves, sequence, qstring

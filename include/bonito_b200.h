@@ -1,0 +1,103 @@
+/*
+ * bonito_b200 -- C ABI of the B200-native chunked forward + decode path.
+ *
+ * The reference (nanoporetech/bonito) is pure Python; its native work on this path is done by
+ * third-party binaries reached from these call sites, which are what each entry point replaces:
+ *
+ *   b200_conv_stem_fwd        torch.nn.Conv1d x2 + activations        bonito/nn.py:221-241
+ *   b200_gemm_fwd             torch.nn.Conv1d (strided, as GEMM),     bonito/nn.py:226,283-298,59-67
+ *                             torch.nn.Linear + Clamp (LinearCRFEncoder), LSTM input projection
+ *   b200_lstm_rec_fwd         koi.lstm.update_graph / torch.nn.LSTM   bonito/crf/model.py:240-246, bonito/nn.py:366-370
+ *   b200_crf_decode           koi.decode.beam_search call contract    bonito/crf/basecall.py:36-40
+ *                             with SeqdistModel.decode_batch maths    bonito/crf/model.py:98-108,196-199
+ *
+ * Conventions: every function returns 0 on success and a negative value on
+ * failure, with a message available from b200_last_error().  All pointers are raw DEVICE pointers
+ * owned by the caller (fp16 = IEEE binary16); the library never allocates or frees caller memory and
+ * keeps no thread-local CUDA state: work is enqueued on the `stream` argument (a cudaStream_t passed
+ * as void*) of the device that is current on the calling thread.  Workspace sizes come from the
+ * *_workspace_bytes() queries.  Safe to call from any host thread.
+ */
+#ifndef BONITO_B200_H
+#define BONITO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ACT_NONE 0
+#define B200_ACT_SWISH 1
+#define B200_ACT_TANH 2
+#define B200_ACT_CLAMP 3 /* clamp(lo, hi), Clamp layer: bonito/nn.py:59-67 */
+
+#define B200_GEMM_AUTO 0 /* tcgen05 (product path) unless B200_GEMM_IMPL=mma is set in the environment */
+#define B200_GEMM_TCGEN05 1
+#define B200_GEMM_MMA_SYNC 2 /* legacy tensor path, kept for on-device cross-checks */
+
+/* Library version (major*10000 + minor*100 + patch). */
+int b200_version(void);
+
+/* Message of the last failure on any thread ("" if none). */
+const char* b200_last_error(void);
+
+/*
+ * Fused conv stem: x[N][L] -> Conv1d(1->c1,k1,pad k1/2)+act1 -> Conv1d(c1->c2,k2,pad k2/2)+act2,
+ * written channels-last and zero padded: out[n][padl + l][c], `lp` rows per chunk (rows outside
+ * [padl, padl+L) are written as zeros).  Weights in torch layout (w1 [c1][1][k1], w2 [c2][c1][k2]),
+ * biases may be NULL.  Supported shapes: (c1,k1,c2,k2) = (16,5,16,5), (4,5,16,5).
+ */
+int b200_conv_stem_fwd(const void* x, int n, int l, int c1, int k1, const void* w1, const void* b1, int act1,
+                       int c2, int k2, const void* w2, const void* b2, int act2, void* out, int lp, int padl,
+                       void* stream);
+
+/*
+ * C = act(A[M,K] * B[N,K]^T + bias) in fp16 with fp32 accumulation.
+ *   A: row stride `lda` elements (lda < K is allowed: overlapping rows = strided convolution windows)
+ *   B: [N][K] row-major (torch Linear / packed Conv1d weight), bias[N] or NULL
+ *   output row of input row r: (outer, inner) = divmod(r, rows_inner); rows with inner >= valid_inner are
+ *   skipped; out_row = inner*stride_inner + outer*stride_outer; C row stride `ldc` elements.
+ *   (identity mapping: rows_inner = valid_inner = M, stride_inner = 1, stride_outer = 0)
+ * Requirements: K % 8 == 0, lda % 8 == 0, N % 8 == 0, ldc % 8 == 0, A/B/C 16-byte aligned.
+ */
+int b200_gemm_fwd(const void* a, long long lda, const void* b, const void* bias, void* c, long long ldc, int m,
+                  int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
+                  long long stride_inner, long long stride_outer, int impl, void* stream);
+
+/*
+ * Cluster size the packed LSTM operands must be laid out for (0: hidden size unsupported).
+ * Supported hidden sizes: 96, 128, 256, 384.
+ */
+int b200_lstm_cluster_size(int hidden);
+
+/*
+ * Recurrent part of one unidirectional LSTM layer over all T steps (h0 = c0 = 0):
+ *   gx  [T][N][4H]  input projection x_t W_ih^T + b_ih + b_hh, columns permuted to
+ *                   [cluster rank][unit/8 block][unit%8][gate i,f,g,o]
+ *   whh [4H][H]     recurrent weights, rows permuted to [cluster rank][unit/8 block][gate][unit%8]
+ *   y   [T][N][H]   h_t in natural unit order
+ * reverse != 0 runs t = T-1..0 (the reference flips the sequence instead: bonito/nn.py:366-370).
+ */
+int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, int hidden, int reverse,
+                      void* stream);
+
+/* Bytes of scratch b200_crf_decode needs for n chunks of t frames. */
+size_t b200_crf_decode_workspace_bytes(int n, int t, int state_len);
+
+/*
+ * Posterior + Viterbi decode of CRF scores.
+ *   scores [N][T][4^(state_len+1)] fp16, no blank column (index = state*4 + dropped_base);
+ *   blank_score: fixed stay score (reference LinearCRFEncoder.blank_score / beam_search default 2.0)
+ *   moves/sequence/qstring: [N][T] bytes; sequence/qstring hold an ASCII char on move frames and 0
+ *   elsewhere, so `to_str` = bytes of the non-zero entries (bonito/crf/basecall.py:50-54);
+ *   quality = phred of the posterior move mass of the emitted base, q = -10 log10(max(1-p,1e-4))*qscale+qbias.
+ */
+int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank_score, float qscale, float qbias,
+                    void* workspace, void* moves, void* sequence, void* qstring, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BONITO_B200_H */

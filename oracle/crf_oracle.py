@@ -1,0 +1,242 @@
+"""
+ORACLE -- TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference's chunked forward + decode path.
+
+Nothing in `bonito_b200/` may import this package; only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s CPU-baseline / reference arm do, and only as the checker / the thing timed as "CPU".
+
+Parity status:
+  * forward (conv -> LSTM stack -> linear -> clamp): PINNED against the reference's own modules
+    (`/root/reference/bonito/nn.py`) imported in the authoring container -- `oracle/make_golden.py`
+    writes `tests/golden/*.npz`, `tests/test_oracle_golden.py` replays them without the reference.
+  * state graph / viterbi path logic: PINNED against `bonito/crf/model.py` (CTC_CRF.idx, viterbi).
+  * posteriors / logZ: the reference delegates them to the closed-source `koi.ctc` (ont-koi==0.5.4,
+    requirements.txt:19), absent here and unpinned by any reference test => "parity unpinned" for
+    that step: the restatement follows the published definition used by the call sites
+    (`bonito/crf/model.py:47-67`): logZ of the sparse transition graph in the Log / Max semiring and
+    posteriors = d logZ / d scores, cross-checked against autograd in tests/test_oracle_crf.py.
+  * koi.decode.beam_search (the CLI decoder): closed source, unpinned; not restated.  The decode oracle
+    is the in-repo decode definition `SeqdistModel.decode_batch` (bonito/crf/model.py:196-199).
+"""
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------------
+# forward path
+# --------------------------------------------------------------------------------------------------
+
+_ACT = {
+    None: lambda x: x,
+    "swish": F.silu,            # bonito/nn.py:54-56  Swish = SiLU
+    "tanh": torch.tanh,
+    "relu": torch.relu,
+}
+
+
+def convolution(x, weight, bias, stride, padding, activation):
+    """Conv1d -> activation (BN already folded).  bonito/nn.py:235-241."""
+    return _ACT[activation](F.conv1d(x, weight, bias, stride=stride, padding=padding))
+
+
+def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, reverse):
+    """
+    Single-layer unidirectional LSTM over x [T, N, I], zero initial state, gate order i,f,g,o
+    (torch.nn.LSTM semantics); `reverse` = flip, run, flip (bonito/nn.py:366-370).
+    """
+    T, N, _ = x.shape
+    H = w_hh.shape[1]
+    if reverse:
+        x = x.flip(0)
+    h = x.new_zeros(N, H)
+    c = x.new_zeros(N, H)
+    gx = x @ w_ih.T + (b_ih + b_hh)
+    out = []
+    for t in range(T):
+        g = gx[t] + h @ w_hh.T
+        i, f, gg, o = g.split(H, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out.append(h)
+    y = torch.stack(out)
+    return y.flip(0) if reverse else y
+
+
+def linear_crf(x, weight, bias, activation=None, scale=None, blank_score=None, n_base=4, expand_blanks=True):
+    """LinearCRFEncoder.forward (bonito/nn.py:283-298) on x [T, N, H]."""
+    s = F.linear(x, weight, bias)
+    s = _ACT[activation](s)
+    if scale is not None:
+        s = s * scale
+    if blank_score is not None and expand_blanks:
+        T, N, C = s.shape
+        s = F.pad(s.view(T, N, C // n_base, n_base), (1, 0, 0, 0, 0, 0, 0, 0), value=blank_score).view(T, N, -1)
+    return s
+
+
+def lstm_crf_forward(weights, spec, x, expand_blanks=False, return_features=False):
+    """
+    Whole LSTM-CRF encoder in fp32 on CPU.
+
+    weights: dict produced by `oracle.synth.make_weights` (torch-layout fp32 tensors)
+    spec:    dict(convs=[(cin,cout,k,stride,pad,act)...], hidden, n_lstm, reverse=[...], state_len, blank_score, clamp)
+    x:       [N, 1, L] float32
+    Returns scores [T, N, C] (reference layout; blanks expanded when `expand_blanks`).
+    """
+    feats = {}
+    h = x
+    for i, (_, _, _, stride, pad, act) in enumerate(spec["convs"]):
+        h = convolution(h, weights[f"conv{i}.weight"], weights[f"conv{i}.bias"], stride, pad, act)
+        feats[f"conv{i}"] = h
+    h = h.permute(2, 0, 1)  # Permute([2,0,1]): NCT -> TNC
+    for i in range(spec["n_lstm"]):
+        h = lstm_layer(h, weights[f"lstm{i}.w_ih"], weights[f"lstm{i}.w_hh"], weights[f"lstm{i}.b_ih"],
+                       weights[f"lstm{i}.b_hh"], spec["reverse"][i])
+        feats[f"lstm{i}"] = h
+    s = linear_crf(h, weights["crf.weight"], weights.get("crf.bias"), blank_score=spec["blank_score"],
+                   expand_blanks=expand_blanks)
+    if spec.get("clamp") is not None:
+        s = s.clamp(*spec["clamp"])  # Clamp: bonito/nn.py:66-67
+    return (s, feats) if return_features else s
+
+
+# --------------------------------------------------------------------------------------------------
+# CRF state graph and semiring DP  (bonito/crf/model.py:30-67, 98-108)
+# --------------------------------------------------------------------------------------------------
+
+def crf_idx(state_len, n_base=4):
+    """idx[s, 0] = s ; idx[s, 1 + j] = j * n_base**(state_len-1) + s // n_base  (bonito/crf/model.py:37-42)."""
+    S = n_base ** state_len
+    s = np.arange(S)
+    idx = np.empty((S, n_base + 1), dtype=np.int64)
+    idx[:, 0] = s
+    for j in range(n_base):
+        idx[:, 1 + j] = j * (S // n_base) + s // n_base
+    return idx
+
+
+def expand_blanks(scores, blank_score, n_base=4):
+    """[..., S*n_base] -> [..., S*(n_base+1)] with the fixed stay score first in each group."""
+    lead = scores.shape[:-1]
+    x = scores.reshape(*lead, -1, n_base)
+    pad = np.full((*lead, x.shape[-2], 1), blank_score, dtype=x.dtype)
+    return np.concatenate([pad, x], axis=-1).reshape(*lead, -1)
+
+
+def _lse(x, axis):
+    m = x.max(axis=axis, keepdims=True)
+    return (m + np.log(np.exp(x - m).sum(axis=axis, keepdims=True))).squeeze(axis)
+
+
+def fwd_bwd(Ms, idx, semiring="log"):
+    """
+    Ms [T, N, S, E] edge scores (E = n_base+1 in-edges of each state), alpha_0 = beta_T = 0.
+    Returns alpha [T+1, N, S], beta [T+1, N, S] with
+        alpha_{t+1}[s] = (+)_e  Ms[t, s, e] (x) alpha_t[idx[s, e]]
+        beta_t[p]      = (+)_{(s,e): idx[s,e]=p}  Ms[t, s, e] (x) beta_{t+1}[s]
+    in the Log ((+) = logsumexp) or Max semiring.  Restates koi.ctc.fwd/bwd_scores_cu_sparse as used at
+    bonito/crf/model.py:57-67.
+    """
+    T, N, S, E = Ms.shape
+    red = _lse if semiring == "log" else (lambda x, axis: x.max(axis=axis))
+    alpha = np.zeros((T + 1, N, S), dtype=Ms.dtype)
+    beta = np.zeros((T + 1, N, S), dtype=Ms.dtype)
+    for t in range(T):
+        alpha[t + 1] = red(Ms[t] + alpha[t][:, idx], axis=-1)
+    # successors of p: gather all (s, e) with idx[s, e] == p
+    succ_s = [[] for _ in range(S)]
+    succ_e = [[] for _ in range(S)]
+    for s in range(S):
+        for e in range(E):
+            succ_s[idx[s, e]].append(s)
+            succ_e[idx[s, e]].append(e)
+    succ_s = np.array(succ_s)
+    succ_e = np.array(succ_e)  # [S, E] (every state has exactly E successors in this graph)
+    for t in range(T - 1, -1, -1):
+        beta[t] = red(Ms[t][:, succ_s, succ_e] + beta[t + 1][:, succ_s], axis=-1)
+    return alpha, beta
+
+
+def logZ(Ms, idx, semiring="log"):
+    alpha, _ = fwd_bwd(Ms, idx, semiring)
+    red = _lse if semiring == "log" else (lambda x, axis: x.max(axis=axis))
+    return red(alpha[-1], axis=-1)
+
+
+def posteriors(Ms, idx):
+    """Log-semiring edge marginals = d logZ / d Ms, shape [T, N, S, E]."""
+    alpha, beta = fwd_bwd(Ms, idx, "log")
+    lz = _lse(alpha[-1], axis=-1)  # [N]
+    x = alpha[:-1][:, :, idx] + Ms + beta[1:][:, :, :, None] - lz[None, :, None, None]
+    return np.exp(x)
+
+
+def viterbi_edges(lp, idx):
+    """
+    Best path through edge scores lp [T, N, S, E] in the Max semiring: returns (state [T, N], edge [T, N]) =
+    the destination state and in-edge taken at every frame.  Tie-breaks: lowest edge index, lowest final state.
+    (The reference takes argmax over koi's Max-semiring gradient, bonito/crf/model.py:98-100.)
+    """
+    T, N, S, E = lp.shape
+    v = np.zeros((N, S), dtype=lp.dtype)
+    bp = np.empty((T, N, S), dtype=np.int64)
+    for t in range(T):
+        cand = lp[t] + v[:, idx]
+        bp[t] = cand.argmax(axis=-1)  # first maximum = lowest edge
+        v = np.take_along_axis(cand, bp[t][..., None], axis=-1)[..., 0]
+    state = v.argmax(axis=-1)
+    states = np.empty((T, N), dtype=np.int64)
+    edges = np.empty((T, N), dtype=np.int64)
+    rows = np.arange(N)
+    for t in range(T - 1, -1, -1):
+        e = bp[t, rows, state]
+        states[t], edges[t] = state, e
+        state = idx[state, e]
+    return states, edges
+
+
+def decode_batch(scores_tnc_blank, state_len, alphabet="NACGT", n_base=4):
+    """
+    SeqdistModel.decode_batch (bonito/crf/model.py:196-199) on blank-expanded scores [T, N, S*5]:
+        post = posteriors(scores.float()) + 1e-8 ; path = viterbi(log post) ; strings.
+    Returns (strings, path [N, T] with 0 = no emission else 1 + base).
+    """
+    T, N, C = scores_tnc_blank.shape
+    idx = crf_idx(state_len, n_base)
+    Ms = scores_tnc_blank.astype(np.float64).reshape(T, N, -1, n_base + 1)
+    post = posteriors(Ms, idx).astype(np.float32)
+    lp = np.log(post + np.float32(1e-8))
+    states, edges = viterbi_edges(lp, idx)
+    # viterbi(): a = s*5 + e ; move = e != 0 ; base = 1 + (a // 5) % 4   (bonito/crf/model.py:101-103)
+    path = np.where(edges != 0, 1 + states % n_base, 0).T  # [N, T]
+    letters = np.frombuffer(alphabet.encode(), dtype="u1")
+    strings = [letters[p[p != 0]].tobytes().decode() for p in path]
+    return strings, path
+
+
+def decode_native(scores_ntc, state_len, blank_score=2.0, qscale=1.0, qbias=0.0, n_base=4):
+    """
+    Oracle for b200_crf_decode: scores [N, T, S*4] (no blanks, fp16-valued) ->
+    (moves, sequence, qstring) uint8 [N, T] with the kernel's output conventions, and the move-mass table.
+    """
+    x = np.asarray(scores_ntc, dtype=np.float64)
+    N, T, C = x.shape
+    idx = crf_idx(state_len, n_base)
+    Ms = expand_blanks(x.transpose(1, 0, 2), blank_score, n_base).reshape(T, N, -1, n_base + 1)
+    post = posteriors(Ms, idx)
+    lp = np.log(post.astype(np.float32) + np.float32(1e-8))
+    states, edges = viterbi_edges(lp, idx)
+    move = edges != 0
+    base = states % n_base
+    # posterior mass of "a move that emits base b" per frame
+    S = Ms.shape[2]
+    mass = post[..., 1:].sum(-1).reshape(T, N, S // n_base, n_base).sum(2)  # [T, N, 4]
+    p = np.take_along_axis(mass, base[..., None], axis=-1)[..., 0]
+    err = np.maximum(1.0 - p, 1e-4)
+    q = np.rint(-10.0 * np.log10(err) * qscale + qbias).astype(np.int64) + 33  # util.phred, bonito/util.py:105-112
+    q = np.clip(q, 33, 126)
+    letters = np.frombuffer(b"ACGT", dtype="u1")
+    moves = move.T.astype(np.uint8)
+    seq = np.where(move, letters[base], 0).T.astype(np.uint8)
+    qual = np.where(move, q, 0).T.astype(np.uint8)
+    return moves, seq, qual, mass.transpose(1, 0, 2)

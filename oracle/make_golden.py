@@ -1,0 +1,130 @@
+"""
+ORACLE -- TEST INFRASTRUCTURE ONLY.  Generate tests/golden/*.npz by running the REFERENCE's own code
+(imported from /root/reference through oracle/reference_shim.py) in the authoring container.
+
+    python -m oracle.make_golden
+
+The fixtures are committed; the GPU box (no /root/reference) only replays them.
+Contents
+  host_logic.npz   chunk / stitch / batchify results of bonito.util on arange signals, CTC_CRF.idx tables,
+                   get_stride, conv length table
+  forward_fast.npz reference module tree (bonito.nn via from_dict, BatchNorm folded by fuse_bn_) forward in
+                   fp32 on CPU: input, every parameter, per-layer features, scores [T,N,C+blanks];
+                   + decode_batch strings (reference glue over the oracle's posteriors stand-in)
+"""
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import reference_shim, synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+class _Read:
+    def __init__(self, rid, n):
+        self.read_id = rid
+        self.signal = np.arange(n, dtype=np.float32)
+
+
+def host_logic(ref):
+    out = {}
+    cases = [(25000, 3996, 492, 6), (100000, 9996, 492, 6), (60000, 12000, 600, 6), (3000, 3996, 492, 6),
+             (25000, 4000, 500, 6), (9996, 9996, 492, 6), (20000, 4000, 0, 5)]
+    meta = []
+    for i, (L, cs, ov, stride) in enumerate(cases):
+        sig = torch.arange(L, dtype=torch.float32)
+        chunks = ref.util.chunk(sig, cs, ov)
+        # frames = every stride-th sample of each chunk, then the reference's stitch_results logic
+        frames = chunks[:, 0, ::stride]
+        if L < cs:
+            stitched = frames[0, :int(np.floor(L / stride))]
+        else:
+            stitched = ref.util.stitch(frames, cs, ov, L, stride)
+            stitched_rev = ref.util.stitch(frames, cs, ov, L, stride, reverse=True)
+            out[f"stitch_rev_{i}"] = stitched_rev.numpy()
+        out[f"chunk_first_{i}"] = chunks[:, 0, 0].numpy()   # first sample of every chunk identifies the window
+        out[f"chunk_shape_{i}"] = np.array(chunks.shape)
+        out[f"stitch_{i}"] = stitched.numpy()
+        meta.append([L, cs, ov, stride])
+    out["cases"] = np.array(meta)
+
+    # batchify / unbatchify keys
+    items = [(f"r{j}", torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) + 100 * j) for j, n in enumerate([3, 5, 1, 7])]
+    batches = list(ref.util.batchify(items, 4))
+    out["batchify_keys"] = np.array(json.dumps([[[k, list(se)] for k, se in keys] for keys, _ in batches]))
+    out["batchify_sizes"] = np.array([v.shape[0] for _, v in batches])
+    rebuilt = list(ref.util.unbatchify(batches))
+    out["unbatchify_keys"] = np.array(json.dumps([k for k, _ in rebuilt]))
+    out["unbatchify_cat"] = torch.cat([v for _, v in rebuilt]).numpy()
+
+    for k in (3, 4, 5):
+        out[f"idx_k{k}"] = ref.crf_model.CTC_CRF(k, ["N", "A", "C", "G", "T"]).idx.numpy()
+    np.savez_compressed(os.path.join(OUT, "host_logic.npz"), **out)
+    print("host_logic.npz", len(out), "arrays")
+
+
+def forward_fast(ref):
+    torch.manual_seed(25)
+    spec = synth.model_spec("fast", n_lstm=2)
+    cfg = synth.model_config(spec, batchnorm=True)
+    model = ref.crf_model.Model(cfg)
+    weights = synth.make_weights(spec, seed=7)
+    sd = synth.state_dict_from_weights(spec, weights)
+    # non-trivial BatchNorm statistics so that fuse_bn_ matters
+    gen = torch.Generator().manual_seed(11)
+    full = model.state_dict()
+    for k in full:
+        if k in sd:
+            full[k] = sd[k]
+        elif k.endswith("bn.weight"):
+            full[k] = 1.0 + 0.2 * torch.randn(full[k].shape, generator=gen)
+        elif k.endswith("bn.bias"):
+            full[k] = 0.1 * torch.randn(full[k].shape, generator=gen)
+        elif k.endswith("running_mean"):
+            full[k] = 0.2 * torch.randn(full[k].shape, generator=gen)
+        elif k.endswith("running_var"):
+            full[k] = 0.5 + torch.rand(full[k].shape, generator=gen)
+    model.load_state_dict(full)
+    model.eval()
+    pre_fusion = {k: v.clone() for k, v in model.state_dict().items()}
+    model.apply(ref.nn.fuse_bn_)           # bonito/cli/basecaller.py:61
+    assert get_stride_ok(ref, model)
+    x = synth.squiggle(3, 1500, seed=5)
+    with torch.inference_mode():
+        scores, feats = model.encoder(x, return_features=True)
+        strings = model.decode_batch(scores)
+    out = {"x": x.numpy(), "scores": scores.numpy(), "strings": np.array(json.dumps(strings)),
+           "config": np.array(json.dumps(cfg)), "stride": np.array(model.stride)}
+    for i, f in enumerate(feats):
+        if i in (1, 2, 4, 5):  # conv1 (stem output), conv2, lstm0, lstm1; the head is `scores`
+            out[f"feat_{i}"] = f.numpy()
+    def compact(a):  # exactly fp16-representable tensors are stored as fp16
+        h = a.astype(np.float16)
+        return h if np.array_equal(h.astype(a.dtype), a) else a
+    for k, v in pre_fusion.items():
+        if "num_batches_tracked" not in k:
+            out["pre." + k] = compact(v.numpy())
+    for k, v in model.state_dict().items():
+        if ".conv." in k:  # only the convolutions change under fuse_bn_
+            out["fused." + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "forward_fast.npz"), **out)
+    print("forward_fast.npz scores", tuple(scores.shape), "strings", [len(s) for s in strings])
+
+
+def get_stride_ok(ref, model):
+    return ref.crf_model.get_stride(model.encoder) == 6 and model.stride == 6
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = reference_shim.load()
+    host_logic(ref)
+    forward_fast(ref)
+
+
+if __name__ == "__main__":
+    main()

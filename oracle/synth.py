@@ -1,0 +1,138 @@
+"""
+ORACLE -- TEST INFRASTRUCTURE ONLY.  Synthetic LSTM-CRF models and signals.
+
+There is no network in the build environment, so the real `dna_r10.4.1_e8.2_400bps_{fast,hac}@v5.0.0`
+checkpoints cannot be fetched (`/root/reference/bonito/cli/download.py:31-83`); every test and benchmark uses
+seeded random weights of the same architecture (shapes: SURVEY.md Appendix A), stored in the reference's own
+on-disk format (`config.toml` + `weights_1.tar`) so the same files drive the reference modules, the oracle
+and the B200 engine.
+"""
+
+import os
+
+import numpy as np
+import torch
+
+SHAPES = {
+    # name: (hidden, state_len)
+    "fast": (96, 3),
+    "hac": (384, 4),
+    "tiny": (96, 3),
+}
+
+
+def model_spec(name="hac", n_lstm=5, stride=6, winlen=19):
+    hidden, state_len = SHAPES[name]
+    return dict(
+        name=name, hidden=hidden, state_len=state_len, n_lstm=n_lstm,
+        convs=[(1, 16, 5, 1, 2, "swish"), (16, 16, 5, 1, 2, "swish"), (16, hidden, winlen, stride, winlen // 2, "tanh")],
+        reverse=[bool((i + 1) % 2) for i in range(n_lstm)],  # 1,0,1,0,1 as in @v4.3.toml:62-95
+        blank_score=2.0, clamp=(-5.0, 5.0), stride=stride,
+    )
+
+
+def model_config(spec, batchnorm=False, batchsize=32, chunksize=3996, overlap=492):
+    """TOML-equivalent dict for `Model(config)` (layout of dna_r10.4.1@v4.3.toml)."""
+    sub = []
+    for cin, cout, k, s, p, act in spec["convs"]:
+        layer = dict(type="convolution", insize=cin, size=cout, bias=True, winlen=k, stride=s, padding=p, activation=act)
+        if batchnorm:
+            layer["norm"] = "batchnorm"
+        sub.append(layer)
+    sub.append(dict(type="permute", dims=[2, 0, 1]))
+    for i in range(spec["n_lstm"]):
+        sub.append(dict(type="lstm", size=spec["hidden"], insize=spec["hidden"], bias=True, reverse=int(spec["reverse"][i])))
+    sub.append(dict(type="linearcrfencoder", insize=spec["hidden"], n_base=4, state_len=spec["state_len"], bias=False,
+                    blank_score=spec["blank_score"]))
+    sub.append(dict(type="clamp", min=spec["clamp"][0], max=spec["clamp"][1]))
+    return {
+        "model": {"package": "bonito.crf"},
+        "labels": {"labels": ["N", "A", "C", "G", "T"]},
+        "input": {"features": 1},
+        "global_norm": {"state_len": spec["state_len"]},
+        "qscore": {"scale": 1.05, "bias": 0.2},
+        "encoder": {"type": "serial", "sublayers": sub},
+        "basecaller": {"batchsize": batchsize, "chunksize": chunksize, "overlap": overlap},
+    }
+
+
+def _orthogonal_blocks(rows, cols, block, gen, gain):
+    w = torch.empty(rows, cols)
+    for r in range(0, rows, block):
+        q, _ = torch.linalg.qr(torch.randn(max(block, cols), max(block, cols), generator=gen))
+        w[r:r + block] = q[:block, :cols]
+    return w * gain
+
+
+def make_weights(spec, seed=25, conv_gain=2.5, lstm_gain=3.0, head_gain=5.0, fp16_values=True):
+    """
+    Seeded, non-degenerate weights (oracle naming).  The reference's own init (orthogonal LSTM blocks,
+    0.5*truncated-normal input bias, zero state bias: bonito/nn.py:362-390) with gains chosen so that
+    decoded sequences vary from chunk to chunk and the +-5 clamp rarely saturates (SURVEY.md hard part H5).
+    With `fp16_values` every tensor is rounded to fp16 (what `model.half()` feeds every implementation).
+    """
+    gen = torch.Generator().manual_seed(seed)
+    H = spec["hidden"]
+    w = {}
+    for i, (cin, cout, k, _, _, _) in enumerate(spec["convs"]):
+        fan_in = cin * k
+        w[f"conv{i}.weight"] = torch.randn(cout, cin, k, generator=gen) * (conv_gain / fan_in ** 0.5)
+        w[f"conv{i}.bias"] = torch.randn(cout, generator=gen) * 0.1
+    for i in range(spec["n_lstm"]):
+        w[f"lstm{i}.w_ih"] = _orthogonal_blocks(4 * H, H, H, gen, lstm_gain)
+        w[f"lstm{i}.w_hh"] = _orthogonal_blocks(4 * H, H, H, gen, lstm_gain)
+        w[f"lstm{i}.b_ih"] = 0.5 * torch.randn(4 * H, generator=gen).clamp(-2, 2)
+        w[f"lstm{i}.b_hh"] = torch.zeros(4 * H)
+    C = 4 ** (spec["state_len"] + 1)
+    w["crf.weight"] = torch.randn(C, H, generator=gen) * (head_gain / H ** 0.5)
+    if fp16_values:
+        w = {k: v.half().float() for k, v in w.items()}
+    return w
+
+
+def state_dict_from_weights(spec, weights, prefix="encoder."):
+    """Oracle naming -> the module tree's state_dict keys (SURVEY.md Appendix A 'State-dict names')."""
+    sd = {}
+    n_conv = len(spec["convs"])
+    for i in range(n_conv):
+        sd[f"{prefix}{i}.conv.weight"] = weights[f"conv{i}.weight"]
+        sd[f"{prefix}{i}.conv.bias"] = weights[f"conv{i}.bias"]
+    base = n_conv + 1  # + Permute
+    for i in range(spec["n_lstm"]):
+        sd[f"{prefix}{base + i}.rnn.weight_ih_l0"] = weights[f"lstm{i}.w_ih"]
+        sd[f"{prefix}{base + i}.rnn.weight_hh_l0"] = weights[f"lstm{i}.w_hh"]
+        sd[f"{prefix}{base + i}.rnn.bias_ih_l0"] = weights[f"lstm{i}.b_ih"]
+        sd[f"{prefix}{base + i}.rnn.bias_hh_l0"] = weights[f"lstm{i}.b_hh"]
+    sd[f"{prefix}{base + spec['n_lstm']}.linear.weight"] = weights["crf.weight"]
+    return sd
+
+
+def write_model_dir(dirname, spec, weights, **config_kwargs):
+    """Write `config.toml` + `weights_1.tar` in the reference's format (bonito/util.py:271-305)."""
+    import toml
+    os.makedirs(dirname, exist_ok=True)
+    with open(os.path.join(dirname, "config.toml"), "w") as fh:
+        toml.dump(model_config(spec, **config_kwargs), fh)
+    torch.save(state_dict_from_weights(spec, weights), os.path.join(dirname, "weights_1.tar"))
+    return dirname
+
+
+def squiggle(n, length, seed=25, dwell=10.0, noise=0.15):
+    """
+    Piecewise-constant synthetic nanopore signal, ~N(0,1) after standardisation:
+    levels ~ N(0,1) held for geometric dwell times (mean `dwell` samples) plus N(0, noise^2).
+    """
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, length), dtype=np.float32)
+    for i in range(n):
+        n_levels = int(length / dwell * 2) + 8
+        dwells = rng.geometric(1.0 / dwell, size=n_levels)
+        levels = rng.standard_normal(n_levels).astype(np.float32)
+        sig = np.repeat(levels, dwells)[:length]
+        out[i] = sig + noise * rng.standard_normal(length).astype(np.float32)
+    return torch.from_numpy(out)[:, None, :]
+
+
+def gaussian_signal(n, length, seed=25):
+    gen = torch.Generator().manual_seed(seed)
+    return torch.randn(n, 1, length, generator=gen)
