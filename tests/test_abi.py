@@ -1,0 +1,41 @@
+"""The C-ABI library loads and exports every symbol include/bonito_b200.h declares (no GPU calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from bonito_b200 import native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "bonito_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _declared() == sorted(native.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(native.lib_path()):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(native.lib_path())
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert native.version() >= 100
+    assert native.load().b200_last_error() == b""
+    assert native.lstm_cluster_size(384) == 8 and native.lstm_cluster_size(96) == 1 and native.lstm_cluster_size(100) == 0
+    assert native.crf_decode_workspace_bytes(2, 10, 3) > 2 * 11 * 64 * 4
+
+
+def test_native_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(native.NativeError, match="CUDA device"):
+        native.require()

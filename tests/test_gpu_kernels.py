@@ -1,0 +1,142 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (bonito_b200.native)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import crf_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def native():
+    from bonito_b200 import native as nat
+    nat.require()
+    return nat
+
+
+def _dev(t):
+    return t.to("cuda", torch.float16).contiguous()
+
+
+def _ref_gemm(a, b, bias, act=None, lo=0.0, hi=0.0):
+    c = a.float() @ b.float().T
+    if bias is not None:
+        c = c + bias.float()
+    c = c.half().float()
+    if act == "tanh":
+        c = torch.tanh(c).half().float()
+    elif act == "swish":
+        c = torch.nn.functional.silu(c).half().float()
+    elif act == "clamp":
+        c = c.clamp(lo, hi)
+    return c
+
+
+@pytest.mark.parametrize("impl_name", ["tcgen05", "mma"])
+@pytest.mark.parametrize("m,n,k,bias,act", [
+    (1000, 384, 304, True, "tanh"),
+    (4096 + 77, 1536, 384, True, None),
+    (3000, 1024, 384, False, "clamp"),
+    (130, 256, 96, False, None),
+    (64, 8, 16, True, "swish"),
+])
+def test_gemm_matches_torch(native, impl_name, m, n, k, bias, act):
+    impl = native.GEMM_TCGEN05 if impl_name == "tcgen05" else native.GEMM_MMA_SYNC
+    g = torch.Generator().manual_seed(m + n + k)
+    a = _dev(torch.randn(m, k, generator=g))
+    b = _dev(torch.randn(n, k, generator=g) / k ** 0.5)
+    bv = _dev(torch.randn(n, generator=g)) if bias else None
+    c = torch.full((m, n), float("nan"), dtype=torch.float16, device="cuda")
+    code = {None: native.ACT_NONE, "tanh": native.ACT_TANH, "swish": native.ACT_SWISH, "clamp": native.ACT_CLAMP}[act]
+    native.gemm(a, k, b, bv, c, n, m, n, k, act=code, lo=-1.0, hi=1.0, impl=impl)
+    torch.cuda.synchronize()
+    ref = _ref_gemm(a.cpu(), b.cpu(), None if bv is None else bv.cpu(), act, -1.0, 1.0)
+    err = (c.float().cpu() - ref).abs().max().item()
+    assert err <= 4e-3, err  # one fp16 ulp at |x| < 4 is 2e-3
+
+
+@pytest.mark.parametrize("impl_name", ["tcgen05", "mma"])
+def test_gemm_overlapping_rows_and_row_remap(native, impl_name):
+    """The strided-conv view: rows 96 elements apart, 304 wide; output rows remapped (n,t) -> (t,n)."""
+    impl = native.GEMM_TCGEN05 if impl_name == "tcgen05" else native.GEMM_MMA_SYNC
+    n_chunks, tp, t_valid, h, k, lda = 3, 40, 37, 384, 304, 96
+    g = torch.Generator().manual_seed(5)
+    flat = _dev(torch.randn(n_chunks * tp * lda + k, generator=g))
+    w = _dev(torch.randn(h, k, generator=g) / k ** 0.5)
+    out = torch.full((t_valid, n_chunks, h), float("nan"), dtype=torch.float16, device="cuda")
+    native.gemm(flat, lda, w, None, out, h, n_chunks * tp, h, k, rows_inner=tp, valid_inner=t_valid,
+                stride_inner=n_chunks, stride_outer=1, impl=impl)
+    torch.cuda.synchronize()
+    rows = torch.stack([flat.cpu()[r * lda:r * lda + k] for r in range(n_chunks * tp)]).float()
+    ref = (rows @ w.cpu().float().T).half().float().view(n_chunks, tp, h)[:, :t_valid].permute(1, 0, 2)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 4e-3, err
+
+
+def test_conv_stem_matches_oracle(native):
+    spec = synth.model_spec("fast")
+    w = synth.make_weights(spec, seed=9)
+    n, L, padl = 3, 1000, 9
+    lp = 1020
+    x = synth.squiggle(n, L, seed=2).half()
+    out = torch.full((n, lp, 16), float("nan"), dtype=torch.float16, device="cuda")
+    native.conv_stem(_dev(x[:, 0]), _dev(w["conv0.weight"]), _dev(w["conv0.bias"]), native.ACT_SWISH,
+                     _dev(w["conv1.weight"]), _dev(w["conv1.bias"]), native.ACT_SWISH, out, lp, padl)
+    torch.cuda.synchronize()
+    h = O.convolution(x.float(), w["conv0.weight"], w["conv0.bias"], 1, 2, "swish")
+    h = O.convolution(h, w["conv1.weight"], w["conv1.bias"], 1, 2, "swish")  # [n,16,L]
+    got = out.float().cpu()
+    assert torch.all(got[:, :padl] == 0) and torch.all(got[:, padl + L:] == 0)
+    err = (got[:, padl:padl + L].permute(0, 2, 1) - h).abs().max().item()
+    assert err <= 1e-2, err
+
+
+@pytest.mark.parametrize("hidden,n,t,reverse", [(96, 5, 40, False), (96, 33, 25, True), (384, 7, 30, False),
+                                                (384, 40, 12, True), (256, 9, 10, False), (128, 4, 10, True)])
+def test_lstm_layer_matches_oracle(native, hidden, n, t, reverse):
+    from bonito_b200.engine import LstmCrfPlan  # only for the permutations' definition
+    g = torch.Generator().manual_seed(hidden + n)
+    H = hidden
+    x = (torch.randn(t, n, H, generator=g) * 0.5).half()
+    w_ih = (torch.randn(4 * H, H, generator=g) / H ** 0.5).half()
+    w_hh = (torch.randn(4 * H, H, generator=g) / H ** 0.5).half()
+    b = (torch.randn(4 * H, generator=g) * 0.3).half()
+    unit = torch.arange(H)
+    perm_ih = (torch.arange(4)[None, :] * H + unit[:, None]).reshape(-1)
+    perm_hh = (torch.arange(H // 8)[:, None, None] * 8 + torch.arange(4)[None, :, None] * H
+               + torch.arange(8)[None, None, :]).reshape(-1)
+    gx = torch.empty(t, n, 4 * H, dtype=torch.float16, device="cuda")
+    native.gemm(_dev(x), H, _dev(w_ih[perm_ih]), _dev(b[perm_ih]), gx, 4 * H, t * n, 4 * H, H)
+    y = torch.full((t, n, H), float("nan"), dtype=torch.float16, device="cuda")
+    native.lstm_rec(gx, _dev(w_hh[perm_hh]), y, t, n, H, reverse)
+    torch.cuda.synchronize()
+    ref = O.lstm_layer(x.float(), w_ih.float(), w_hh.float(), b.float(), torch.zeros(4 * H), reverse)
+    err = (y.float().cpu() - ref).abs().max().item()
+    assert err <= 5e-3, err
+
+
+@pytest.mark.parametrize("state_len,n,t", [(3, 4, 200), (4, 3, 333), (4, 2, 1666), (5, 2, 60), (3, 1, 1)])
+def test_crf_decode_matches_oracle(native, state_len, n, t):
+    from bonito_b200.engine import CrfDecoder
+    g = torch.Generator().manual_seed(state_len * 100 + t)
+    c = 4 ** (state_len + 1)
+    scores = (torch.randn(n, t, c, generator=g) * 1.7).clamp(-5, 5).half()
+    moves, seq, qual = CrfDecoder()(scores.cuda(), state_len, blank_score=2.0, qscale=1.05, qbias=0.2)
+    torch.cuda.synchronize()
+    o_moves, o_seq, o_qual, _ = O.decode_native(scores.float().numpy(), state_len, 2.0, 1.05, 0.2)
+    assert np.array_equal(moves.cpu().numpy(), o_moves)
+    assert np.array_equal(seq.cpu().numpy(), o_seq)
+    dq = np.abs(qual.cpu().numpy().astype(int) - o_qual.astype(int))
+    assert dq.max() <= 1 and (dq != 0).mean() < 0.01
+    assert o_moves.mean() > 0.2  # the case is not degenerate
+
+
+def test_error_reporting(native):
+    with pytest.raises(native.NativeError, match="multiples of 8"):
+        a = torch.zeros(16, 12, dtype=torch.float16, device="cuda")
+        native.gemm(a, 12, a, None, a, 12, 16, 16, 12)
+    with pytest.raises(native.NativeError, match="not supported"):
+        z = torch.zeros(4, 4, 4 * 100, dtype=torch.float16, device="cuda")
+        native.lstm_rec(z, z, z, 4, 4, 100, False)
