@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""
+bench.py -- raw-signal samples/sec basecalled (forward + decode) on synthetic chunks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): hac-shaped LSTM-CRF (H=384, 5-mer scores, seeded random weights -- the
+real checkpoint needs the network), batch 512 chunks per GPU, 10 000-sample chunks trimmed to a stride multiple
+(9996) exactly as `_load_model(use_koi=True)` does (bonito/util.py:288-291).  A step = one batch through
+conv stem -> strided conv GEMM -> 5 x (input GEMM + persistent LSTM) -> CRF linear + clamp -> CRF decode.
+
+  value  whole-job samples/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e    the same through the reference-facing call `compute_scores(model, batch)` with HOST float32 input:
+         fp16 cast into pinned memory, H2D, forward, decode, D2H of moves/sequence/qstring inside the timing
+  roofline / stages: per-kernel CUDA-event durations recorded inside the timed region
+
+Multi-GPU: chunks shard by batch (one process per GPU, weights broadcast once over NCCL, no steady-state
+collective) => weak scaling.
+--impl reference: the reference's PyTorch-CPU execution of the same path (oracle/cpu_reference.py) on the host
+cores, a bounded sample of the workload per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "raw-signal samples/sec basecalled (forward+decode), 10k-sample chunks, hac-shaped LSTM-CRF"
+CHUNK = 10000
+BATCH = 512
+MODEL = "hac"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=p["hbm_gbs"], tflops=p["bf16_tflops_sustained"], tflops_burst=p["bf16_tflops"], source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tflops=1400.0, tflops_burst=1590.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, flag in zip(names, r[3:7]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(device, rank, world):
+    from bonito_b200.crf.model import Model
+    from oracle import synth
+    spec = synth.model_spec(MODEL)
+    weights = synth.make_weights(spec, seed=25)
+    cfg = synth.model_config(spec, batchsize=BATCH, chunksize=CHUNK, overlap=500)
+    model = Model(cfg)
+    if rank == 0:
+        model.load_state_dict(synth.state_dict_from_weights(spec, weights))
+    chunksize = CHUNK - CHUNK % model.stride
+    model.use_koi(batchsize=BATCH, chunksize=chunksize, quantize=False)
+    model = model.half().eval().to(device)
+    if world > 1:  # the one collective of the path: weights from rank 0 (NCCL over NVLink)
+        import torch.distributed as dist
+        for p in model.parameters():
+            dist.broadcast(p.data, src=0)
+    return model, spec, weights, chunksize
+
+
+def cpu_baseline(spec, weights, chunksize, n_chunks=16, threads=None):
+    from oracle import synth
+    from oracle.cpu_reference import CpuReferenceModel
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    ref = CpuReferenceModel(spec, weights)
+    x = synth.squiggle(n_chunks, chunksize, seed=25)
+    ref.forward(x[:2])  # warm-up
+    _, _, _, tf, td = ref.basecall_batch(x)
+    samples = n_chunks * chunksize
+    return {"value": samples / (tf + td), "unit": "samples/s", "cores": threads, "kind": "port",
+            "forward_only": samples / tf,
+            "sample": f"{n_chunks} chunks x {chunksize} samples, torch {torch.__version__} fp32 modules as bonito.nn builds "
+                      f"them + numpy posterior-Viterbi decode (forward {tf:.2f}s, decode {td:.2f}s)"}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: PyTorch-CPU path on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import synth
+    spec = synth.model_spec(MODEL)
+    weights = synth.make_weights(spec, seed=25)
+    chunksize = CHUNK - CHUNK % 6
+    from oracle.cpu_reference import CpuReferenceModel
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    ref = CpuReferenceModel(spec, weights)
+    n_chunks = 8
+    x = synth.squiggle(n_chunks, chunksize, seed=25)
+    for _ in range(max(args.warmup, 1)):
+        ref.forward(x[:2])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref.basecall_batch(x)
+    dt = time.perf_counter() - t0
+    value = n_chunks * chunksize * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{MODEL}-shaped LSTM-CRF, {chunksize}-sample chunks, forward+decode",
+                   "sample_chunks_per_step": n_chunks},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_chunks} chunks x {chunksize} samples per step"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from bonito_b200.crf.basecall import compute_scores
+    from bonito_b200.decode import _decoder
+    from oracle import synth
+
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    peaks = load_peaks()
+    model, spec, weights, chunksize = build_model(device, rank, world)
+    N, L = args.batch, chunksize
+    host_batch = synth.squiggle(64, L, seed=100 + rank).repeat(N // 64 + 1, 1, 1)[:N].contiguous()  # float32 host
+    x_dev = host_batch.to(device, torch.float16)
+    plan = model.native_plan(device)
+    T = plan.frames(L)
+    qs = model.config["qscore"]
+
+    def step_resident(events=None):
+        scores = plan.forward(x_dev, events=events)
+        return _decoder(scores, spec["state_len"], blank_score=plan.blank_score, qscale=qs["scale"], qbias=qs["bias"],
+                        events=events)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.inference_mode():
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        events = []
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for _ in range(args.steps):
+            step_resident(events)
+        t_end.record()
+        barrier()
+        elapsed_ms = t_start.elapsed_time(t_end)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # end to end through the reference-facing call, host float32 batch in, host byte arrays out
+        for _ in range(2):
+            compute_scores(model, host_batch, scale=qs["scale"], offset=qs["bias"])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = compute_scores(model, host_batch, scale=qs["scale"], offset=qs["bias"])
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        stage_ms = {}
+        for name, a, b in events:
+            stage_ms.setdefault(name, []).append(a.elapsed_time(b))
+        per_step = {k: sum(v) / args.steps for k, v in stage_ms.items()}
+        launches = {k: len(v) // args.steps for k, v in stage_ms.items()}
+        step_ms = elapsed_ms / args.steps
+        dominant = max(per_step, key=per_step.get)
+        H = spec["hidden"]
+        flops = {  # algorithmic FLOPs per launch
+            "lstm_rec": 2.0 * N * T * 4 * H * H,
+            "lstm_in_gemm": 2.0 * N * T * 4 * H * H,
+            "conv_gemm": 2.0 * N * T * H * plan.k3 * plan.c2,
+            "crf_gemm": 2.0 * N * T * plan.n_scores * H,
+        }
+        bytes_ = {  # algorithmic HBM bytes per launch
+            "conv_stem": N * L * 2 + N * L * plan.c2 * 2,
+            "crf_decode": N * T * plan.n_scores * 2 + 3 * N * T,
+        }
+        if dominant in flops:
+            dur = per_step[dominant] / launches[dominant] * 1e-3
+            ach = flops[dominant] / dur / 1e12
+            roof = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"] + " (sustained bf16 GEMM)",
+                    "launch_ms": dur * 1e3, "share_of_step": per_step[dominant] / step_ms}
+        else:
+            dur = per_step[dominant] / launches[dominant] * 1e-3
+            ach = bytes_[dominant] / dur / 1e9
+            roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["source"],
+                    "launch_ms": dur * 1e3, "share_of_step": per_step[dominant] / step_ms}
+        total_flops = sum(flops[k] * launches.get(k, 0) for k in flops)
+        line = {
+            "metric": METRIC, "value": world * N * L * args.steps / (elapsed_ms * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"{MODEL}-shaped LSTM-CRF (H={H}, {spec['n_lstm']} LSTM, {plan.n_scores} scores/frame), "
+                                   f"batch {N}/GPU, {CHUNK}->{L}-sample chunks ({T} frames), forward+decode",
+                       "weights": "seeded synthetic (oracle/synth.py)", "l2": "per-step tensors (0.16-2.6 GB) exceed the 126 MB L2",
+                       "parallelism": f"chunk-sharded replicas x{world}"},
+            "e2e": {"value": world * N * L * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": N * L * 2, "d2h_bytes_per_step": 3 * N * T, "ms_per_step": e2e_ms / args.steps,
+                    "api": "bonito_b200.crf.basecall.compute_scores(model, float32 host batch)"},
+            "gpu_launches": sum(len(v) for v in stage_ms.values()),
+            "roofline": roof,
+            "stages_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},
+            "model_tflops_per_s": total_flops / (step_ms * 1e-3) / 1e12,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(spec, weights, chunksize)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,7 +34,8 @@ struct DecodeSmem {
     static constexpr size_t kBuf = 0;                                  // float [2][S]
     static constexpr size_t kVit = kBuf + 2 * S * sizeof(float);       // float [2][S]
     static constexpr size_t kUnion = kVit + 2 * S * sizeof(float);     // float [2][4*S]  |  u8 [TB][S]
-    static constexpr size_t kPart = kUnion + 2 * 4 * S * sizeof(float);
+    static constexpr size_t kUnionBytes = (2 * 4 * S * sizeof(float) > (size_t)TB * S) ? 2 * 4 * S * sizeof(float) : (size_t)TB * S;
+    static constexpr size_t kPart = kUnion + kUnionBytes;
     static constexpr size_t kRed = kPart + 2 * NW * 4 * sizeof(float);
     static constexpr size_t kRedI = kRed + NW * sizeof(float);
     static constexpr size_t kOut = kRedI + NW * sizeof(int) + 16;      // u8 [3][T]

@@ -53,6 +53,25 @@ def _dev16(t, device):
     return None if t is None else t.to(device=device, dtype=torch.float16).contiguous()
 
 
+class _Stage:
+    """Context manager recording a CUDA event pair around one kernel launch (no-op without a sink)."""
+
+    def __init__(self, name, sink):
+        self.name, self.sink = name, sink
+
+    def __enter__(self):
+        if self.sink is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if self.sink is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            self.sink.append((self.name, self.start, end))
+        return False
+
+
 class LstmCrfPlan:
     """Packed weights + cached buffers for one LSTM-CRF encoder on one device."""
 
@@ -154,8 +173,14 @@ class LstmCrfPlan:
             self._bufs[key]["stem"][-tail:].zero_()
         return self._bufs[key]
 
-    def forward(self, x, out=None, gemm_impl=native.GEMM_AUTO, return_features=False):
-        """x: [N, 1, L] (or [N, L]) fp16 CUDA -> scores [N, T, C] fp16 (no blank column)."""
+    def forward(self, x, out=None, gemm_impl=native.GEMM_AUTO, return_features=False, events=None):
+        """
+        x: [N, 1, L] (or [N, L]) fp16 CUDA -> scores [N, T, C] fp16 (no blank column).
+        `events`: optional list; (stage, start, end) CUDA events on the current stream are appended per kernel.
+        """
+        def stage(name):
+            return _Stage(name, events)
+
         if x.dim() == 3:
             x = x[:, 0, :]
         x = x.to(device=self.device, dtype=torch.float16).contiguous()
@@ -165,20 +190,24 @@ class LstmCrfPlan:
         T, Tp, Lp = b["T"], b["Tp"], b["Lp"]
         feats = {}
 
-        native.conv_stem(x, self.w1, self.b1, self.act1, self.w2, self.b2, self.act2, b["stem"], Lp, self.pad3)
+        with stage("conv_stem"):
+            native.conv_stem(x, self.w1, self.b1, self.act1, self.w2, self.b2, self.act2, b["stem"], Lp, self.pad3)
         if return_features:
             feats["stem"] = b["stem"][:N * Lp * self.c2].view(N, Lp, self.c2)[:, self.pad3:self.pad3 + L].clone()
 
         # strided conv: rows r = n*Tp + t are windows of k3*c2 elements, s3*c2 apart; out[t][n][:]
         cur, nxt = b["ya"], b["yb"]
-        native.gemm(b["stem"], self.s3 * self.c2, self.w3, self.b3, cur, H, N * Tp, H, self.k3 * self.c2,
-                    act=self.act3, rows_inner=Tp, valid_inner=T, stride_inner=N, stride_outer=1, impl=gemm_impl)
+        with stage("conv_gemm"):
+            native.gemm(b["stem"], self.s3 * self.c2, self.w3, self.b3, cur, H, N * Tp, H, self.k3 * self.c2,
+                        act=self.act3, rows_inner=Tp, valid_inner=T, stride_inner=N, stride_outer=1, impl=gemm_impl)
         if return_features:
             feats["conv"] = cur.clone()
 
         for i, layer in enumerate(self.lstm):
-            native.gemm(cur, H, layer["wih"], layer["bias"], b["gx"], 4 * H, T * N, 4 * H, H, impl=gemm_impl)
-            native.lstm_rec(b["gx"], layer["whh"], nxt, T, N, H, layer["reverse"])
+            with stage("lstm_in_gemm"):
+                native.gemm(cur, H, layer["wih"], layer["bias"], b["gx"], 4 * H, T * N, 4 * H, H, impl=gemm_impl)
+            with stage("lstm_rec"):
+                native.lstm_rec(b["gx"], layer["whh"], nxt, T, N, H, layer["reverse"])
             cur, nxt = nxt, cur
             if return_features:
                 feats[f"lstm{i}"] = cur.clone()
@@ -186,9 +215,10 @@ class LstmCrfPlan:
         if out is None:
             out = torch.empty(N, T, self.n_scores, dtype=torch.float16, device=self.device)
         # rows r = t*N + n -> out[n][t][:]
-        native.gemm(cur, H, self.wl, self.bl, out, self.n_scores, T * N, self.n_scores, H,
-                    act=self.act_l, lo=self.lo, hi=self.hi,
-                    rows_inner=N, valid_inner=N, stride_inner=T, stride_outer=1, impl=gemm_impl)
+        with stage("crf_gemm"):
+            native.gemm(cur, H, self.wl, self.bl, out, self.n_scores, T * N, self.n_scores, H,
+                        act=self.act_l, lo=self.lo, hi=self.hi,
+                        rows_inner=N, valid_inner=N, stride_inner=T, stride_outer=1, impl=gemm_impl)
         return (out, feats) if return_features else out
 
 
@@ -202,7 +232,7 @@ class CrfDecoder:
     def __init__(self):
         self._ws = None
 
-    def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0):
+    def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0, events=None):
         n, t, c = scores.shape
         if c != 4 ** (state_len + 1):
             raise ValueError(f"scores width {c} does not match state_len {state_len}")
@@ -211,5 +241,6 @@ class CrfDecoder:
         if self._ws is None or self._ws.numel() < need or self._ws.device != scores.device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=scores.device)
         outs = [torch.empty(n, t, dtype=torch.uint8, device=scores.device) for _ in range(3)]
-        native.crf_decode(scores, state_len, blank_score, qscale, qbias, self._ws, *outs)
+        with _Stage("crf_decode", events):
+            native.crf_decode(scores, state_len, blank_score, qscale, qbias, self._ws, *outs)
         return tuple(outs)  # moves, sequence, qstring

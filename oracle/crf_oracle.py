@@ -34,15 +34,22 @@ _ACT = {
 }
 
 
-def convolution(x, weight, bias, stride, padding, activation):
+def _r16(x, fp16):
+    """Round to fp16 and back: the storage rounding points of the reference's half-precision path."""
+    return x.half().float() if fp16 else x
+
+
+def convolution(x, weight, bias, stride, padding, activation, fp16=False):
     """Conv1d -> activation (BN already folded).  bonito/nn.py:235-241."""
-    return _ACT[activation](F.conv1d(x, weight, bias, stride=stride, padding=padding))
+    return _r16(_ACT[activation](_r16(F.conv1d(x, weight, bias, stride=stride, padding=padding), fp16)), fp16)
 
 
-def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, reverse):
+def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, reverse, fp16=False):
     """
     Single-layer unidirectional LSTM over x [T, N, I], zero initial state, gate order i,f,g,o
     (torch.nn.LSTM semantics); `reverse` = flip, run, flip (bonito/nn.py:366-370).
+    With `fp16` the input projection and every h_t are rounded to fp16 (fp32 accumulation and cell state),
+    the rounding points of a half-precision LSTM.
     """
     T, N, _ = x.shape
     H = w_hh.shape[1]
@@ -50,13 +57,13 @@ def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, reverse):
         x = x.flip(0)
     h = x.new_zeros(N, H)
     c = x.new_zeros(N, H)
-    gx = x @ w_ih.T + (b_ih + b_hh)
+    gx = _r16(x @ w_ih.T + (b_ih + b_hh), fp16)
     out = []
     for t in range(T):
         g = gx[t] + h @ w_hh.T
         i, f, gg, o = g.split(H, dim=1)
         c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
-        h = torch.sigmoid(o) * torch.tanh(c)
+        h = _r16(torch.sigmoid(o) * torch.tanh(c), fp16)
         out.append(h)
     y = torch.stack(out)
     return y.flip(0) if reverse else y
@@ -74,7 +81,7 @@ def linear_crf(x, weight, bias, activation=None, scale=None, blank_score=None, n
     return s
 
 
-def lstm_crf_forward(weights, spec, x, expand_blanks=False, return_features=False):
+def lstm_crf_forward(weights, spec, x, expand_blanks=False, return_features=False, fp16=False):
     """
     Whole LSTM-CRF encoder in fp32 on CPU.
 
@@ -82,19 +89,24 @@ def lstm_crf_forward(weights, spec, x, expand_blanks=False, return_features=Fals
     spec:    dict(convs=[(cin,cout,k,stride,pad,act)...], hidden, n_lstm, reverse=[...], state_len, blank_score, clamp)
     x:       [N, 1, L] float32
     Returns scores [T, N, C] (reference layout; blanks expanded when `expand_blanks`).
+    `fp16=True` keeps fp32 arithmetic but rounds every stored activation to fp16 (what `model.half()` stores).
     """
     feats = {}
     h = x
     for i, (_, _, _, stride, pad, act) in enumerate(spec["convs"]):
-        h = convolution(h, weights[f"conv{i}.weight"], weights[f"conv{i}.bias"], stride, pad, act)
+        h = convolution(h, weights[f"conv{i}.weight"], weights[f"conv{i}.bias"], stride, pad, act, fp16)
         feats[f"conv{i}"] = h
     h = h.permute(2, 0, 1)  # Permute([2,0,1]): NCT -> TNC
     for i in range(spec["n_lstm"]):
         h = lstm_layer(h, weights[f"lstm{i}.w_ih"], weights[f"lstm{i}.w_hh"], weights[f"lstm{i}.b_ih"],
-                       weights[f"lstm{i}.b_hh"], spec["reverse"][i])
+                       weights[f"lstm{i}.b_hh"], spec["reverse"][i], fp16)
         feats[f"lstm{i}"] = h
-    s = linear_crf(h, weights["crf.weight"], weights.get("crf.bias"), blank_score=spec["blank_score"],
-                   expand_blanks=expand_blanks)
+    s = linear_crf(_r16(h, fp16), weights["crf.weight"], weights.get("crf.bias"), blank_score=spec["blank_score"],
+                   expand_blanks=False)
+    s = _r16(s, fp16)
+    if expand_blanks:
+        T_, N_, C_ = s.shape
+        s = F.pad(s.view(T_, N_, C_ // 4, 4), (1, 0), value=spec["blank_score"]).view(T_, N_, -1)
     if spec.get("clamp") is not None:
         s = s.clamp(*spec["clamp"])  # Clamp: bonito/nn.py:66-67
     return (s, feats) if return_features else s

@@ -85,12 +85,14 @@ def test_conv_stem_matches_oracle(native):
     native.conv_stem(_dev(x[:, 0]), _dev(w["conv0.weight"]), _dev(w["conv0.bias"]), native.ACT_SWISH,
                      _dev(w["conv1.weight"]), _dev(w["conv1.bias"]), native.ACT_SWISH, out, lp, padl)
     torch.cuda.synchronize()
-    h = O.convolution(x.float(), w["conv0.weight"], w["conv0.bias"], 1, 2, "swish")
-    h = O.convolution(h, w["conv1.weight"], w["conv1.bias"], 1, 2, "swish")  # [n,16,L]
     got = out.float().cpu()
     assert torch.all(got[:, :padl] == 0) and torch.all(got[:, padl + L:] == 0)
-    err = (got[:, padl:padl + L].permute(0, 2, 1) - h).abs().max().item()
-    assert err <= 1e-2, err
+    for fp16, tol in ((True, 8e-3), (False, 3e-2)):  # same rounding points: ~1 fp16 ulp; pure fp32: a few
+        h = O.convolution(x.float(), w["conv0.weight"], w["conv0.bias"], 1, 2, "swish", fp16)
+        h = O.convolution(h, w["conv1.weight"], w["conv1.bias"], 1, 2, "swish", fp16)  # [n,16,L]
+        err = (got[:, padl:padl + L].permute(0, 2, 1) - h).abs().max().item()
+        print("conv stem fp16-oracle" if fp16 else "conv stem fp32-oracle", err, "max|h|", h.abs().max().item())
+        assert err <= tol, err
 
 
 @pytest.mark.parametrize("hidden,n,t,reverse", [(96, 5, 40, False), (96, 33, 25, True), (384, 7, 30, False),
