@@ -39,6 +39,10 @@ BATCH = 512
 MODEL = "hac"
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -113,12 +117,15 @@ def build_model(device, rank, world):
 def cpu_baseline(spec, weights, chunksize, n_chunks=16, threads=None):
     from oracle import synth
     from oracle.cpu_reference import CpuReferenceModel
-    threads = threads or os.cpu_count()
+    threads = threads or min(os.cpu_count(), 32)
     torch.set_num_threads(threads)
+    log(f"cpu baseline: {n_chunks} chunks on {threads} threads (host has {os.cpu_count()})")
     ref = CpuReferenceModel(spec, weights)
     x = synth.squiggle(n_chunks, chunksize, seed=25)
     ref.forward(x[:2])  # warm-up
+    log("cpu baseline: warm-up done")
     _, _, _, tf, td = ref.basecall_batch(x)
+    log(f"cpu baseline: forward {tf:.2f}s decode {td:.2f}s")
     samples = n_chunks * chunksize
     return {"value": samples / (tf + td), "unit": "samples/s", "cores": threads, "kind": "port",
             "forward_only": samples / tf,
@@ -135,7 +142,7 @@ def run_reference(args, rank, world):
     weights = synth.make_weights(spec, seed=25)
     chunksize = CHUNK - CHUNK % 6
     from oracle.cpu_reference import CpuReferenceModel
-    threads = os.cpu_count()
+    threads = min(os.cpu_count(), 32)
     torch.set_num_threads(threads)
     ref = CpuReferenceModel(spec, weights)
     n_chunks = 8
@@ -194,6 +201,7 @@ def main():
     N, L = args.batch, chunksize
     host_batch = synth.squiggle(64, L, seed=100 + rank).repeat(N // 64 + 1, 1, 1)[:N].contiguous()  # float32 host
     x_dev = host_batch.to(device, torch.float16)
+    log("model built")
     plan = model.native_plan(device)
     T = plan.frames(L)
     qs = model.config["qscore"]
@@ -213,6 +221,7 @@ def main():
         for _ in range(max(args.warmup, 3)):
             step_resident()
         barrier()
+        log("warm-up done")
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -224,6 +233,7 @@ def main():
         t_end.record()
         barrier()
         elapsed_ms = t_start.elapsed_time(t_end)
+        log(f"resident: {elapsed_ms / args.steps:.2f} ms/step")
         clocks = sampler.stop() if rank == 0 else None
 
         # end to end through the reference-facing call, host float32 batch in, host byte arrays out
@@ -236,6 +246,7 @@ def main():
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         barrier()
+        log(f"e2e: {e2e_ms / args.steps:.2f} ms/step")
 
     if world > 1:
         t = torch.tensor([elapsed_ms, e2e_ms], device=device, dtype=torch.float64)

@@ -87,7 +87,7 @@ def test_conv_stem_matches_oracle(native):
     torch.cuda.synchronize()
     got = out.float().cpu()
     assert torch.all(got[:, :padl] == 0) and torch.all(got[:, padl + L:] == 0)
-    for fp16, tol in ((True, 8e-3), (False, 3e-2)):  # same rounding points: ~1 fp16 ulp; pure fp32: a few
+    for fp16, tol in ((True, 1.6e-2), (False, 3e-2)):  # max|h| ~ 33 here: one fp16 ulp is 1.56e-2
         h = O.convolution(x.float(), w["conv0.weight"], w["conv0.bias"], 1, 2, "swish", fp16)
         h = O.convolution(h, w["conv1.weight"], w["conv1.bias"], 1, 2, "swish", fp16)  # [n,16,L]
         err = (got[:, padl:padl + L].permute(0, 2, 1) - h).abs().max().item()
