@@ -14,6 +14,10 @@ int launch_conv_stem(const __half* x, int N, int L, int C1, int K1, const __half
 int lstm_rec_cluster_size(int H);
 int launch_lstm_rec(const __half* gx, const __half* whh, __half* y, int T, int N, int H, int reverse,
                     cudaStream_t stream);
+bool lstm_rec_tc_supported(int hidden);
+int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
+                       cudaStream_t stream);
+int launch_tmem_probe(float* out, cudaStream_t stream);
 size_t crf_decode_workspace_bytes(int N, int T, int state_len);
 int launch_crf_decode(const __half* scores, int N, int T, int state_len, float blank, float qscale, float qbias,
                       void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream);
@@ -81,8 +85,18 @@ int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, in
     B200_REQUIRE(gx && whh && y, "lstm_rec: null pointer argument");
     B200_REQUIRE(t >= 0 && n >= 0, "lstm_rec: bad sizes t=%d n=%d", t, n);
     if (t == 0 || n == 0) return 0;
+    const char* env = getenv("B200_LSTM_IMPL");
+    const bool force_mma = env && strcmp(env, "mma") == 0;
+    if (!force_mma && lstm_rec_tc_supported(hidden))
+        return launch_lstm_rec_tc((const __half*)gx, (const __half*)whh, (__half*)y, t, n, hidden, reverse,
+                                  (cudaStream_t)stream);
     return launch_lstm_rec((const __half*)gx, (const __half*)whh, (__half*)y, t, n, hidden, reverse,
                            (cudaStream_t)stream);
+}
+
+int b200_debug_tmem_probe(void* out, void* stream) {
+    B200_REQUIRE(out != nullptr, "tmem_probe: null pointer argument");
+    return launch_tmem_probe((float*)out, (cudaStream_t)stream);
 }
 
 size_t b200_crf_decode_workspace_bytes(int n, int t, int state_len) {

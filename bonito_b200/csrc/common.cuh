@@ -38,13 +38,16 @@ void b200_set_error(const char* fmt, ...);
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
-
-// tanh with ~1e-6 abs error (the SFU tanh.approx is ~5e-4, too coarse for 1e-3 parity)
+// sigmoid / tanh from one ex2 and one rcp each (2 SFU ops, no IEEE division): abs error ~2e-7, far below fp16
+// resolution (the single-op tanh.approx is ~5e-4, too coarse for 1e-3 parity).
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + exp2f(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_f(float x) {
-    float e = __expf(-2.0f * fabsf(x));
-    float r = (1.0f - e) / (1.0f + e);
-    return copysignf(r, x);
+    return fmaf(2.0f, rcp_approx(1.0f + exp2f(-2.8853900817779268f * x)), -1.0f);
 }
 
 __device__ __forceinline__ float swish_f(float x) { return x * sigmoid_f(x); }

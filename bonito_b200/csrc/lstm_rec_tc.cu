@@ -1,0 +1,290 @@
+// Persistent recurrent part of one LSTM layer on the 5th-generation tensor cores (hac: H = 384).
+// Reference semantics: bonito/nn.py:353-415 (torch.nn.LSTM, gate order i,f,g,o, zero initial state, optional
+// time reversal), the span `Model.use_koi` hands to koi.lstm (bonito/crf/model.py:240-246).
+//
+// Decomposition: a cluster of CS = 8 CTAs owns one batch tile of NB = 32 chunks for all T steps; CTA `rank` owns
+// hidden units [48*rank, 48*rank+48) = 192 gate rows of W_hh.
+//   * W_hh slice lives in TENSOR MEMORY for the whole kernel as the UMMA A operand: two 128-lane blocks
+//     (rows 0..127 and rows 64..191; fp16 pairs per 32-bit column => 192 columns each).  The tensor core re-reads
+//     all of it every step, which shared memory (128 B/clk) could not feed at N = 32.
+//   * h_{t-1} tile [32 chunks x 384] sits in shared memory, K-major SWIZZLE_128B, as the UMMA B operand
+//     (double buffered by step parity).
+//   * per step one thread issues 48 tcgen05.mma (M=128, N=32, K=16) -> gate pre-activations in TMEM (64 columns);
+//     six epilogue warps pull them with tcgen05.ld.16x256b -- the mma-accumulator fragment, so with rows ordered
+//     [8 units x (i,f,g,o)] one thread holds all four gates of a (unit, chunk) -- add the prefetched input
+//     projection, update (c, h) in registers, and push the new h slice as 16-byte chunks straight into the h tile
+//     of all 8 CTAs of the cluster (st.async: the store itself completes transaction bytes on the destination's
+//     mbarrier, so there is no fence and no arrive on the sender) and into Y[t].  No __threadfence, no cluster
+//     barrier, no L2 round trip on the recurrence.
+//
+// Packed operands are the same as for the mma.sync kernel (lstm_rec.cu): whh [CS][UPC/8][gate][8][H],
+// gx [T][N][CS][UPC/8][8][gate], y [T][N][H].
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int NB = 32;             // chunks per cluster
+constexpr int H = 384;
+constexpr int CS = 8;
+constexpr int UPC = H / CS;        // 48 units per CTA
+constexpr int ROWS = 4 * UPC;      // 192 gate rows per CTA
+constexpr int KB = H / 64;         // 6 k-blocks of 64
+constexpr int NEPI = ROWS / 32;    // 6 epilogue warps, one 32-row block each
+constexpr int THREADS = 256;
+constexpr uint32_t HTILE = KB * NB * 128;          // 24576 B
+constexpr uint32_t COL_A1 = 0, COL_A2 = 192, COL_D1 = 384, COL_D2 = 416, TMEM_COLS = 512;
+constexpr uint32_t OFF_H = 0, OFF_STAGE = 2 * HTILE, OFF_BARS = OFF_STAGE + NEPI * NB * 16;
+constexpr uint32_t SMEM_USED = OFF_BARS + 64 + 1024;
+// the kernel owns all 512 TMEM columns: ask for more than half of the SM's shared memory so that two CTAs can
+// never be co-resident (a second tcgen05.alloc on the same SM would spin forever)
+constexpr uint32_t SMEM_BYTES = SMEM_USED > 120 * 1024 ? SMEM_USED : 120 * 1024;
+
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(THREADS, 1)
+lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh, __half* __restrict__ y, int T, int N,
+                   int reverse) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_hfull0 = base + OFF_BARS, bar_hfull1 = bar_hfull0 + 8, bar_dfull = bar_hfull0 + 16;
+    const uint32_t tmem_slot = bar_hfull0 + 24;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+    const int group = blockIdx.x / CS;
+    const int n0 = group * NB;
+
+    if (tid == 0) {
+        mbar_init(bar_hfull0, 1);
+        mbar_init(bar_hfull1, 1);
+        mbar_init(bar_dfull, 1);
+        mbar_fence_init();
+        // every fill of an h tile is NB*H*2 bytes of st.async traffic from the 8 CTAs of the cluster
+        if (T > 1) mbar_expect_tx(bar_hfull1, HTILE);   // filled during step 0
+        if (T > 2) mbar_expect_tx(bar_hfull0, HTILE);   // filled during step 1
+    }
+    if (warp == 4) tc_alloc(tmem_slot, TMEM_COLS);
+    // h_{-1} = 0
+    for (int i = tid; i < (int)(HTILE / 16); i += THREADS) reinterpret_cast<uint4*>(gbase + OFF_H)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 24);
+
+    // resident weights -> TMEM (lane = gate row, column c = fp16 pair (2c, 2c+1) of that row)
+    if (warp < 4) {
+        const __half* wsrc = whh + (size_t)rank * ROWS * H;
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+            const int row = blk * 64 + warp * 32 + lane;
+            const uint4* src = reinterpret_cast<const uint4*>(wsrc + (size_t)row * H);
+#pragma unroll 1
+            for (int c = 0; c < H / 64; ++c) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint4 w = __ldg(src + c * 8 + i);
+                    v[4 * i + 0] = w.x; v[4 * i + 1] = w.y; v[4 * i + 2] = w.z; v[4 * i + 3] = w.w;
+                }
+                tc_st_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (blk ? COL_A2 : COL_A1) + c * 32, v);
+            }
+        }
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cluster_sync_all();  // every CTA's barriers are initialised before anyone arrives remotely
+
+    if (warp == 4) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc_f16(128, NB);
+            for (int step = 0; step < T; ++step) {
+                const int p = step & 1;
+                if (step > 0) {
+                    const uint32_t bar = p ? bar_hfull1 : bar_hfull0;
+                    mbar_wait(bar, (uint32_t)((((step + 1) >> 1) - 1) & 1));
+                    if (step + 2 < T) mbar_expect_tx(bar, HTILE);  // re-arm: this buffer is filled again during step+1
+                    fence_proxy_async_smem();
+                }
+                tc_fence_after();
+                const uint32_t hb = base + OFF_H + p * HTILE;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint64_t bdesc = tc_smem_desc_sw128(hb + kb * (NB * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acol = (uint32_t)(kb * 4 + k) * 8;
+                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                        tc_mma_ts(tmem_base + COL_D1, tmem_base + COL_A1 + acol, bdesc + 2u * k, idesc, acc);
+                        tc_mma_ts(tmem_base + COL_D2, tmem_base + COL_A2 + acol, bdesc + 2u * k, idesc, acc);
+                    }
+                }
+                tc_commit(bar_dfull);
+            }
+        }
+    } else if (warp != 5) {
+        // ===== epilogue warps: warp 0..3 -> row blocks 0..3 (accumulator D1), warps 6,7 -> blocks 4,5 (D2) =====
+        const int blk = warp < 4 ? warp : warp - 2;
+        const int quarter = warp & 3;
+        const uint32_t dcol = warp < 4 ? COL_D1 : COL_D2;
+        const int r = lane >> 2, q = lane & 3;
+        const size_t gx_col = (size_t)rank * ROWS + (size_t)blk * 32 + r * 4;
+        __half* stage = reinterpret_cast<__half*>(gbase + OFF_STAGE) + blk * NB * 8;  // [32 chunks][8 units]
+        const int u0 = (int)rank * UPC + blk * 8;                                       // first unit of this block
+        const uint32_t dst_off = (uint32_t)(u0 >> 6) * (NB * 128) + sw128_offset(lane, (u0 & 63) >> 3);
+        float c_state[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c_state[j][0] = c_state[j][1] = 0.f;
+
+        // input pre-activations are prefetched one step ahead: they never sit on the recurrence's critical path
+        auto load_gx = [&](int step, uint2 (&dst)[4][2]) {
+            const int t = reverse ? (T - 1 - step) : step;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = n0 + 8 * j + 2 * q + e;
+                    dst[j][e] = (n < N) ? __ldg(reinterpret_cast<const uint2*>(gx + ((size_t)t * N + n) * 4 * H + gx_col))
+                                        : make_uint2(0, 0);
+                }
+        };
+        uint2 g[4][2], gn[4][2];
+        load_gx(0, g);
+
+        for (int step = 0; step < T; ++step) {
+            const int t = reverse ? (T - 1 - step) : step;
+            const int p = step & 1;
+            if (step + 1 < T) load_gx(step + 1, gn);
+            mbar_wait(bar_dfull, (uint32_t)(step & 1));
+            tc_fence_after();
+            uint32_t a[16], b[16];
+            tc_ld_16x256b_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + dcol, a);        // rows 0..15: gates i, f
+            tc_ld_16x256b_x4(tmem_base + ((uint32_t)(quarter * 32 + 16) << 16) + dcol, b);   // rows 16..31: gates g, o
+            tc_wait_ld();
+            tc_fence_before();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const __half2 g01 = *reinterpret_cast<const __half2*>(&g[j][e].x);
+                    const __half2 g23 = *reinterpret_cast<const __half2*>(&g[j][e].y);
+                    const float ai = __uint_as_float(a[4 * j + e]) + __low2float(g01);
+                    const float af = __uint_as_float(a[4 * j + 2 + e]) + __high2float(g01);
+                    const float ag = __uint_as_float(b[4 * j + e]) + __low2float(g23);
+                    const float ao = __uint_as_float(b[4 * j + 2 + e]) + __high2float(g23);
+                    const float c = sigmoid_f(af) * c_state[j][e] + sigmoid_f(ai) * tanh_f(ag);
+                    c_state[j][e] = c;
+                    const float h = sigmoid_f(ao) * tanh_f(c);
+                    stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(h);
+                }
+            __syncwarp();
+            const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];  // chunk `lane`: its 8 units
+            const int n = n0 + lane;
+            if (step + 1 < T) {
+                const uint32_t dst = base + OFF_H + (p ^ 1) * HTILE + dst_off;
+                const uint32_t bar = (p ^ 1) ? bar_hfull1 : bar_hfull0;
+#pragma unroll
+                for (int d = 0; d < CS; ++d) st_async_v4(mapa(dst, d), chunk, mapa(bar, d));
+            }
+            if (n < N) *reinterpret_cast<uint4*>(y + ((size_t)t * N + n) * H + u0) = chunk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { g[j][0] = gn[j][0]; g[j][1] = gn[j][1]; }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // nobody leaves while peers may still write into this CTA's shared memory
+    if (warp == 4) tc_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- TMEM layout probe (debug / self-test) ----------------------------------------------------------
+// out[0 .. 128*32): what each thread receives from tcgen05.ld.16x256b.x4 (lanes +0 and +16 of its quarter) after
+//                   lane L / column c was filled with 100*L + c through tcgen05.st.32x32b;
+// out[4096 .. 4096 + 128*32): D = A * B^T with A (128 x 16, fp16) taken from TMEM, B (32 x 16) from swizzled smem.
+__global__ void __launch_bounds__(128, 1) tmem_probe_kernel(float* __restrict__ out) {
+    __shared__ __align__(1024) unsigned char btile[NB * 128];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+    if (warp == 0) tc_alloc(smem_u32(&slot), 128);
+    for (int i = tid; i < NB * 128 / 4; i += 128) reinterpret_cast<uint32_t*>(btile)[i] = 0;
+    __syncthreads();
+    // B[n][k] = ((n + k) % 5) * 0.5, K-major SW128 rows (only the first 32 B of each 128-B row are used)
+    if (tid < NB) {
+        __half row[16];
+        for (int k = 0; k < 16; ++k) row[k] = __float2half(((tid + k) % 5) * 0.5f);
+        for (int c = 0; c < 2; ++c)
+            *reinterpret_cast<uint4*>(btile + sw128_offset(tid, c)) = *reinterpret_cast<uint4*>(row + 8 * c);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = slot;
+    {
+        uint32_t v[32];
+        for (int c = 0; c < 32; ++c) v[c] = __float_as_uint((float)(100 * tid + c));
+        tc_st_32x32b_x32(tb + ((uint32_t)(warp * 32) << 16) + 0, v);
+        // A[i][k] = ((i % 7) + k) * 0.25 packed as fp16 pairs in columns 32..39
+        uint32_t w[32];
+        for (int c = 0; c < 32; ++c) {
+            __half2 h2 = __floats2half2_rn(((tid % 7) + 2 * c) * 0.25f, ((tid % 7) + 2 * c + 1) * 0.25f);
+            w[c] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        tc_st_32x32b_x32(tb + ((uint32_t)(warp * 32) << 16) + 32, w);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        tc_mma_ts(tb + 64, tb + 32, tc_smem_desc_sw128(smem_u32(btile)), tc_idesc_f16(128, NB), 0u);
+        tc_commit(smem_u32(&bar));
+    }
+    {
+        uint32_t a[16], b[16];
+        tc_ld_16x256b_x4(tb + ((uint32_t)(warp * 32) << 16) + 0, a);
+        tc_ld_16x256b_x4(tb + ((uint32_t)(warp * 32 + 16) << 16) + 0, b);
+        tc_wait_ld();
+        for (int i = 0; i < 16; ++i) {
+            out[tid * 32 + i] = __uint_as_float(a[i]);
+            out[tid * 32 + 16 + i] = __uint_as_float(b[i]);
+        }
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    {
+        uint32_t d[32];
+        tc_ld_32x32b_x32(tb + ((uint32_t)(warp * 32) << 16) + 64, d);
+        tc_wait_ld();
+        for (int c = 0; c < 32; ++c) out[4096 + tid * 32 + c] = __uint_as_float(d[c]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc_dealloc(tb, 128);
+}
+
+}  // namespace
+
+bool lstm_rec_tc_supported(int hidden) { return hidden == H; }
+
+int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
+                       cudaStream_t stream) {
+    B200_REQUIRE(hidden == H, "lstm_rec_tc: hidden size %d is not supported (384)", hidden);
+    B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const int groups = (N + NB - 1) / NB;
+    lstm_rec_tc_kernel<<<groups * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, T, N, reverse);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_tmem_probe(float* out, cudaStream_t stream) {
+    tmem_probe_kernel<<<1, 128, 0, stream>>>(out);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

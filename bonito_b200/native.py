@@ -28,6 +28,7 @@ SIGNATURES = {
                               c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_void_p]),
     "b200_lstm_cluster_size": (c_int, [c_int]),
     "b200_lstm_rec_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200_debug_tmem_probe": (c_int, [c_void_p, c_void_p]),
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_crf_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -128,6 +129,16 @@ def lstm_rec(gx, whh, y, t, n, hidden, reverse):
                                    int(bool(reverse)), _stream())
     _check(rc, "b200_lstm_rec_fwd")
     return y
+
+
+def tmem_probe():
+    """Run the TMEM convention probe; returns a float32 CPU tensor of 8192 values."""
+    lib = require()
+    out = torch.zeros(8192, dtype=torch.float32, device="cuda")
+    rc = lib.b200_debug_tmem_probe(_ptr(out), _stream())
+    _check(rc, "b200_debug_tmem_probe")
+    torch.cuda.synchronize()
+    return out.cpu()
 
 
 def crf_decode_workspace_bytes(n, t, state_len):

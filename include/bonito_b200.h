@@ -79,9 +79,18 @@ int b200_lstm_cluster_size(int hidden);
  *   whh [4H][H]     recurrent weights, rows permuted to [cluster rank][unit/8 block][gate][unit%8]
  *   y   [T][N][H]   h_t in natural unit order
  * reverse != 0 runs t = T-1..0 (the reference flips the sequence instead: bonito/nn.py:366-370).
+ * hidden = 384 runs the tcgen05 kernel (W_hh resident in tensor memory, h exchanged through distributed shared
+ * memory); other sizes, or B200_LSTM_IMPL=mma in the environment, run the mma.sync kernel.
  */
 int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, int hidden, int reverse,
                       void* stream);
+
+/*
+ * Self-test of the tensor-memory conventions the tcgen05 kernels rely on (fragment layout of
+ * tcgen05.ld.16x256b, fp16-pair packing of a TMEM-resident A operand).  out: 8192 floats (device);
+ * interpreted by tests/test_gpu_kernels.py::test_tmem_conventions.
+ */
+int b200_debug_tmem_probe(void* out, void* stream);
 
 /* Bytes of scratch b200_crf_decode needs for n chunks of t frames. */
 size_t b200_crf_decode_workspace_bytes(int n, int t, int state_len);

@@ -119,6 +119,41 @@ def test_lstm_layer_matches_oracle(native, hidden, n, t, reverse):
     assert err <= 5e-3, err
 
 
+def test_tmem_conventions(native):
+    """tcgen05.ld.16x256b fragment layout and the fp16-pair packing of a TMEM-resident A operand."""
+    out = native.tmem_probe().numpy()
+    frag = out[:4096].reshape(128, 32)
+    tid = np.arange(128)
+    warp, lane = tid // 32, tid % 32
+    want = np.zeros((128, 32), dtype=np.float32)
+    for half in range(2):
+        for j in range(4):
+            for hi in range(2):
+                for e in range(2):
+                    row = warp * 32 + 16 * half + lane // 4 + 8 * hi
+                    col = 8 * j + 2 * (lane % 4) + e
+                    want[:, 16 * half + 4 * j + 2 * hi + e] = 100 * row + col
+    if not np.array_equal(frag, want):
+        print("observed fragment of thread 0..7:\n", frag[:8])
+    assert np.array_equal(frag, want)
+    d = out[4096:].reshape(128, 32)
+    i, n, k = np.arange(128)[:, None, None], np.arange(32)[None, :, None], np.arange(16)[None, None, :]
+    ref = ((((i % 7) + k) * 0.25) * (((n + k) % 5) * 0.5)).sum(-1)
+    if not np.allclose(d, ref, atol=1e-3):
+        print("observed D[0:4, 0:8]:\n", d[:4, :8], "\nexpected:\n", ref[:4, :8])
+    np.testing.assert_allclose(d, ref, atol=1e-3)
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+@pytest.mark.parametrize("n,t,reverse", [(7, 30, False), (40, 12, True), (64, 50, False), (33, 3, True)])
+def test_lstm_384_both_kernels(native, monkeypatch, impl, n, t, reverse):
+    if impl == "mma":
+        monkeypatch.setenv("B200_LSTM_IMPL", "mma")
+    else:
+        monkeypatch.delenv("B200_LSTM_IMPL", raising=False)
+    test_lstm_layer_matches_oracle(native, 384, n, t, reverse)
+
+
 @pytest.mark.parametrize("state_len,n,t", [(3, 4, 200), (4, 3, 333), (4, 2, 1666), (5, 2, 60), (3, 1, 1)])
 def test_crf_decode_matches_oracle(native, state_len, n, t):
     from bonito_b200.engine import CrfDecoder
