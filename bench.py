@@ -108,9 +108,8 @@ def build_model(device, rank, world):
     model.use_koi(batchsize=BATCH, chunksize=chunksize, quantize=False)
     model = model.half().eval().to(device)
     if world > 1:  # the one collective of the path: weights from rank 0 (NCCL over NVLink)
-        import torch.distributed as dist
-        for p in model.parameters():
-            dist.broadcast(p.data, src=0)
+        from bonito_b200.distributed import broadcast_parameters
+        broadcast_parameters(model, src=0)
     return model, spec, weights, chunksize
 
 

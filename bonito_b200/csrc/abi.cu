@@ -18,6 +18,7 @@ bool lstm_rec_tc_supported(int hidden);
 int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
                        cudaStream_t stream);
 int launch_tmem_probe(float* out, cudaStream_t stream);
+int copy_lstm_timeline(long long* host_out, int max_steps);
 size_t crf_decode_workspace_bytes(int N, int T, int state_len);
 int launch_crf_decode(const __half* scores, int N, int T, int state_len, float blank, float qscale, float qbias,
                       void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream);
@@ -97,6 +98,11 @@ int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, in
 int b200_debug_tmem_probe(void* out, void* stream) {
     B200_REQUIRE(out != nullptr, "tmem_probe: null pointer argument");
     return launch_tmem_probe((float*)out, (cudaStream_t)stream);
+}
+
+int b200_debug_lstm_timeline(long long* host_out, int max_steps) {
+    B200_REQUIRE(host_out != nullptr && max_steps > 0, "lstm_timeline: bad arguments");
+    return copy_lstm_timeline(host_out, max_steps);
 }
 
 size_t b200_crf_decode_workspace_bytes(int n, int t, int state_len) {

@@ -19,6 +19,8 @@
 //
 // Packed operands are the same as for the mma.sync kernel (lstm_rec.cu): whh [CS][UPC/8][gate][8][H],
 // gx [T][N][CS][UPC/8][8][gate], y [T][N][H].
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -39,6 +41,15 @@ constexpr uint32_t SMEM_USED = OFF_BARS + 64 + 1024;
 // never be co-resident (a second tcgen05.alloc on the same SM would spin forever)
 constexpr uint32_t SMEM_BYTES = SMEM_USED > 120 * 1024 ? SMEM_USED : 120 * 1024;
 
+// timeline of CTA 0 (VARIANT 3): per step, SM-clock stamps of
+//   [0] h tile complete (MMA thread)   [1] MMAs issued + committed   [2] accumulator ready (epilogue warp 0)
+//   [3] TMEM loaded   [4] cell update done   [5] h chunk sent        [6] same as [2] for warp 7   [7] [5] for warp 7
+constexpr int TL_STEPS = 256;
+__device__ long long g_timeline[TL_STEPS][8];
+
+// VARIANT is a timing-experiment knob (B200_LSTM_DEBUG): 0 = product; 1 = all eight copies of the h chunk go to the
+// CTA's own tile (no inter-SM traffic; wrong results); 2 = cell update replaced by a sum (no SFU work; wrong results).
+template <int VARIANT>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(THREADS, 1)
 lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh, __half* __restrict__ y, int T, int N,
                    int reverse) {
@@ -108,6 +119,7 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
                     if (step + 2 < T) mbar_expect_tx(bar, HTILE);  // re-arm: this buffer is filled again during step+1
                     fence_proxy_async_smem();
                 }
+                if (VARIANT == 3 && blockIdx.x == 0 && step < TL_STEPS) g_timeline[step][0] = clock64();
                 tc_fence_after();
                 const uint32_t hb = base + OFF_H + p * HTILE;
 #pragma unroll
@@ -122,6 +134,7 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
                     }
                 }
                 tc_commit(bar_dfull);
+                if (VARIANT == 3 && blockIdx.x == 0 && step < TL_STEPS) g_timeline[step][1] = clock64();
             }
         }
     } else if (warp != 5) {
@@ -158,12 +171,15 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
             const int p = step & 1;
             if (step + 1 < T) load_gx(step + 1, gn);
             mbar_wait(bar_dfull, (uint32_t)(step & 1));
+            const bool tl = VARIANT == 3 && blockIdx.x == 0 && step < TL_STEPS && lane == 0 && (warp == 0 || warp == 7);
+            if (tl) g_timeline[step][warp == 0 ? 2 : 6] = clock64();
             tc_fence_after();
             uint32_t a[16], b[16];
             tc_ld_16x256b_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + dcol, a);        // rows 0..15: gates i, f
             tc_ld_16x256b_x4(tmem_base + ((uint32_t)(quarter * 32 + 16) << 16) + dcol, b);   // rows 16..31: gates g, o
             tc_wait_ld();
             tc_fence_before();
+            if (tl && warp == 0) g_timeline[step][3] = clock64();
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -174,21 +190,32 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
                     const float af = __uint_as_float(a[4 * j + 2 + e]) + __high2float(g01);
                     const float ag = __uint_as_float(b[4 * j + e]) + __low2float(g23);
                     const float ao = __uint_as_float(b[4 * j + 2 + e]) + __high2float(g23);
-                    const float c = sigmoid_f(af) * c_state[j][e] + sigmoid_f(ai) * tanh_f(ag);
+                    float c, h;
+                    if (VARIANT == 2) {
+                        c = 0.25f * (af + ai + ag) + 0.5f * c_state[j][e];
+                        h = 0.1f * (ao + c);
+                    } else {
+                        c = sigmoid_f(af) * c_state[j][e] + sigmoid_f(ai) * tanh_f(ag);
+                        h = sigmoid_f(ao) * tanh_f(c);
+                    }
                     c_state[j][e] = c;
-                    const float h = sigmoid_f(ao) * tanh_f(c);
                     stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(h);
                 }
             __syncwarp();
+            if (tl && warp == 0) g_timeline[step][4] = clock64();
             const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];  // chunk `lane`: its 8 units
             const int n = n0 + lane;
             if (step + 1 < T) {
                 const uint32_t dst = base + OFF_H + (p ^ 1) * HTILE + dst_off;
                 const uint32_t bar = (p ^ 1) ? bar_hfull1 : bar_hfull0;
 #pragma unroll
-                for (int d = 0; d < CS; ++d) st_async_v4(mapa(dst, d), chunk, mapa(bar, d));
+                for (int d = 0; d < CS; ++d) {
+                    const uint32_t peer = VARIANT == 1 ? rank : (uint32_t)d;
+                    st_async_v4(mapa(dst, peer), chunk, mapa(bar, peer));
+                }
             }
             if (n < N) *reinterpret_cast<uint4*>(y + ((size_t)t * N + n) * H + u0) = chunk;
+            if (tl) g_timeline[step][warp == 0 ? 5 : 7] = clock64();
 #pragma unroll
             for (int j = 0; j < 4; ++j) { g[j][0] = gn[j][0]; g[j][1] = gn[j][1]; }
             __syncwarp();
@@ -276,11 +303,29 @@ bool lstm_rec_tc_supported(int hidden) { return hidden == H; }
 int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
                        cudaStream_t stream) {
     B200_REQUIRE(hidden == H, "lstm_rec_tc: hidden size %d is not supported (384)", hidden);
-    B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     const int groups = (N + NB - 1) / NB;
-    lstm_rec_tc_kernel<<<groups * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, T, N, reverse);
+    const char* dbg = getenv("B200_LSTM_DEBUG");
+    const int variant = dbg ? atoi(dbg) : 0;
+#define LAUNCH_VARIANT(v)                                                                                          \
+    do {                                                                                                           \
+        B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<v>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                             (int)SMEM_BYTES));                                                    \
+        lstm_rec_tc_kernel<v><<<groups * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, T, N, reverse);            \
+    } while (0)
+    if (variant == 3) LAUNCH_VARIANT(3);
+    else if (variant == 1) LAUNCH_VARIANT(1);
+    else if (variant == 2) LAUNCH_VARIANT(2);
+    else LAUNCH_VARIANT(0);
+#undef LAUNCH_VARIANT
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+int copy_lstm_timeline(long long* host_out, int max_steps) {
+    const int n = max_steps < TL_STEPS ? max_steps : TL_STEPS;
+    B200_CHECK_CUDA(cudaDeviceSynchronize());
+    B200_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 8 * n));
+    return n;
 }
 
 int launch_tmem_probe(float* out, cudaStream_t stream) {

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b200_lstm_cluster_size": (c_int, [c_int]),
     "b200_lstm_rec_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_debug_tmem_probe": (c_int, [c_void_p, c_void_p]),
+    "b200_debug_lstm_timeline": (c_int, [c_void_p, c_int]),
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_crf_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -139,6 +140,16 @@ def tmem_probe():
     _check(rc, "b200_debug_tmem_probe")
     torch.cuda.synchronize()
     return out.cpu()
+
+
+def lstm_timeline(steps=256):
+    """[steps, 8] int64 SM-clock stamps recorded by CTA 0 of the last lstm_rec launch under B200_LSTM_DEBUG=3."""
+    import numpy as np
+    buf = np.zeros((steps, 8), dtype=np.int64)
+    n = load().b200_debug_lstm_timeline(buf.ctypes.data_as(c_void_p), steps)
+    if n < 0:
+        _check(n, "b200_debug_lstm_timeline")
+    return buf[:n]
 
 
 def crf_decode_workspace_bytes(n, t, state_len):

@@ -92,6 +92,13 @@ int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, in
  */
 int b200_debug_tmem_probe(void* out, void* stream);
 
+/*
+ * Timing aid: after a b200_lstm_rec_fwd launched with B200_LSTM_DEBUG=3 in the environment, copies the SM-clock
+ * stamps CTA 0 recorded for its first steps ([step][8] int64, HOST buffer; see lstm_rec_tc.cu).  Returns the
+ * number of steps copied (<= 256) or a negative error.
+ */
+int b200_debug_lstm_timeline(long long* host_out, int max_steps);
+
 /* Bytes of scratch b200_crf_decode needs for n chunks of t frames. */
 size_t b200_crf_decode_workspace_bytes(int n, int t, int state_len);
 
