@@ -298,6 +298,7 @@ def main():
             "gpu_launches": sum(len(v) for v in stage_ms.values()),
             "roofline": roof,
             "stages_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},
+            "lstm_rec_launch_ms": [round(v, 3) for v in stage_ms.get("lstm_rec", [])[:5]],
             "model_tflops_per_s": total_flops / (step_ms * 1e-3) / 1e12,
             "clocks": clocks,
         }

@@ -19,6 +19,8 @@ int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, in
                        cudaStream_t stream);
 int launch_tmem_probe(float* out, cudaStream_t stream);
 int copy_lstm_timeline(long long* host_out, int max_steps);
+int lstm_rec_tc_max_clusters();
+int launch_mma_bench(int ts_mode, int n, int iters, int chains, int blocks, long long* out, cudaStream_t stream);
 size_t crf_decode_workspace_bytes(int N, int T, int state_len);
 int launch_crf_decode(const __half* scores, int N, int T, int state_len, float blank, float qscale, float qbias,
                       void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream);
@@ -100,9 +102,17 @@ int b200_debug_tmem_probe(void* out, void* stream) {
     return launch_tmem_probe((float*)out, (cudaStream_t)stream);
 }
 
+int b200_debug_lstm_max_clusters(void) { return lstm_rec_tc_max_clusters(); }
+
 int b200_debug_lstm_timeline(long long* host_out, int max_steps) {
     B200_REQUIRE(host_out != nullptr && max_steps > 0, "lstm_timeline: bad arguments");
     return copy_lstm_timeline(host_out, max_steps);
+}
+
+int b200_debug_mma_bench(int ts_mode, int n, int iters, int chains, int blocks, void* out, void* stream) {
+    B200_REQUIRE(out != nullptr && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && chains >= 1 && chains * n <= 448,
+                 "mma_bench: bad arguments");
+    return launch_mma_bench(ts_mode, n, iters, chains, blocks, (long long*)out, (cudaStream_t)stream);
 }
 
 size_t b200_crf_decode_workspace_bytes(int n, int t, int state_len) {

@@ -43,7 +43,7 @@ constexpr uint32_t SMEM_BYTES = SMEM_USED > 120 * 1024 ? SMEM_USED : 120 * 1024;
 
 // timeline of CTA 0 (VARIANT 3): per step, SM-clock stamps of
 //   [0] h tile complete (MMA thread)   [1] MMAs issued + committed   [2] accumulator ready (epilogue warp 0)
-//   [3] TMEM loaded   [4] cell update done   [5] h chunk sent        [6] same as [2] for warp 7   [7] [5] for warp 7
+//   [3] TMEM loaded   [4] cell update done   [5] h chunk sent        [6] %globaltimer (ns) at [0]     [7] [5] for warp 7
 constexpr int TL_STEPS = 256;
 __device__ long long g_timeline[TL_STEPS][8];
 
@@ -108,18 +108,22 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
     cluster_sync_all();  // every CTA's barriers are initialised before anyone arrives remotely
 
     if (warp == 4) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc_idesc_f16(128, NB);
-            for (int step = 0; step < T; ++step) {
-                const int p = step & 1;
+        // ===== MMA issuer: the whole warp walks the steps, one elected lane issues =====
+        constexpr uint32_t idesc = tc_idesc_f16(128, NB);
+        for (int step = 0; step < T; ++step) {
+            const int p = step & 1;
+            if (step > 0) mbar_wait(p ? bar_hfull1 : bar_hfull0, (uint32_t)((((step + 1) >> 1) - 1) & 1));
+            if (elect_one_sync()) {
                 if (step > 0) {
-                    const uint32_t bar = p ? bar_hfull1 : bar_hfull0;
-                    mbar_wait(bar, (uint32_t)((((step + 1) >> 1) - 1) & 1));
-                    if (step + 2 < T) mbar_expect_tx(bar, HTILE);  // re-arm: this buffer is filled again during step+1
+                    if (step + 2 < T) mbar_expect_tx(p ? bar_hfull1 : bar_hfull0, HTILE);  // re-arm for the fill in step+1
                     fence_proxy_async_smem();
                 }
-                if (VARIANT == 3 && blockIdx.x == 0 && step < TL_STEPS) g_timeline[step][0] = clock64();
+                if (VARIANT == 3 && blockIdx.x == 0) {
+                    g_timeline[step % TL_STEPS][0] = clock64();
+                    unsigned long long gt;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                    g_timeline[step % TL_STEPS][6] = (long long)gt;
+                }
                 tc_fence_after();
                 const uint32_t hb = base + OFF_H + p * HTILE;
 #pragma unroll
@@ -134,8 +138,9 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
                     }
                 }
                 tc_commit(bar_dfull);
-                if (VARIANT == 3 && blockIdx.x == 0 && step < TL_STEPS) g_timeline[step][1] = clock64();
+                if (VARIANT == 3 && blockIdx.x == 0) g_timeline[step % TL_STEPS][1] = clock64();
             }
+            __syncwarp();
         }
     } else if (warp != 5) {
         // ===== epilogue warps: warp 0..3 -> row blocks 0..3 (accumulator D1), warps 6,7 -> blocks 4,5 (D2) =====
@@ -171,15 +176,16 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
             const int p = step & 1;
             if (step + 1 < T) load_gx(step + 1, gn);
             mbar_wait(bar_dfull, (uint32_t)(step & 1));
-            const bool tl = VARIANT == 3 && blockIdx.x == 0 && step < TL_STEPS && lane == 0 && (warp == 0 || warp == 7);
-            if (tl) g_timeline[step][warp == 0 ? 2 : 6] = clock64();
+            const bool tl = VARIANT == 3 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7);
+            const int ts = step % TL_STEPS;
+            if (tl && warp == 0) g_timeline[ts][2] = clock64();
             tc_fence_after();
             uint32_t a[16], b[16];
             tc_ld_16x256b_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + dcol, a);        // rows 0..15: gates i, f
             tc_ld_16x256b_x4(tmem_base + ((uint32_t)(quarter * 32 + 16) << 16) + dcol, b);   // rows 16..31: gates g, o
             tc_wait_ld();
             tc_fence_before();
-            if (tl && warp == 0) g_timeline[step][3] = clock64();
+            if (tl && warp == 0) g_timeline[ts][3] = clock64();
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -202,7 +208,7 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
                     stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(h);
                 }
             __syncwarp();
-            if (tl && warp == 0) g_timeline[step][4] = clock64();
+            if (tl && warp == 0) g_timeline[ts][4] = clock64();
             const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];  // chunk `lane`: its 8 units
             const int n = n0 + lane;
             if (step + 1 < T) {
@@ -215,7 +221,7 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
                 }
             }
             if (n < N) *reinterpret_cast<uint4*>(y + ((size_t)t * N + n) * H + u0) = chunk;
-            if (tl) g_timeline[step][warp == 0 ? 5 : 7] = clock64();
+            if (tl) g_timeline[ts][warp == 0 ? 5 : 7] = clock64();
 #pragma unroll
             for (int j = 0; j < 4; ++j) { g[j][0] = gn[j][0]; g[j][1] = gn[j][1]; }
             __syncwarp();
@@ -319,6 +325,26 @@ int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, in
 #undef LAUNCH_VARIANT
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+// how many 8-CTA clusters of the recurrent kernel the device can hold at once (GPC packing decides)
+int lstm_rec_tc_max_clusters() {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS * 64);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaFuncSetAttribute(lstm_rec_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+        return -1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_rec_tc_kernel<0>, &cfg) != cudaSuccess) return -1;
+    return n;
 }
 
 int copy_lstm_timeline(long long* host_out, int max_steps) {

@@ -4,6 +4,21 @@
 
 #include "common.cuh"
 
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler then knows the guarded code runs in a
+// single thread and feeds UTCHMMA / UTMALDG from uniform registers directly instead of wrapping every instruction in
+// an R2UR + ELECT + BRA.U.ANY loop (~48 cycles per MMA issue).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));

@@ -30,6 +30,8 @@ SIGNATURES = {
     "b200_lstm_rec_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_debug_tmem_probe": (c_int, [c_void_p, c_void_p]),
     "b200_debug_lstm_timeline": (c_int, [c_void_p, c_int]),
+    "b200_debug_lstm_max_clusters": (c_int, []),
+    "b200_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_crf_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -140,6 +142,15 @@ def tmem_probe():
     _check(rc, "b200_debug_tmem_probe")
     torch.cuda.synchronize()
     return out.cpu()
+
+
+def mma_bench(ts_mode, n, iters=960, chains=1, blocks=1):
+    """(issue cycles, issue-to-completion cycles, ns) of tcgen05.mma M=128 x N=n x K=16 over `chains` accumulators."""
+    lib = require()
+    out = torch.zeros(3, dtype=torch.int64, device="cuda")
+    _check(lib.b200_debug_mma_bench(int(ts_mode), n, iters, chains, blocks, _ptr(out), _stream()), "b200_debug_mma_bench")
+    torch.cuda.synchronize()
+    return out.cpu().tolist()
 
 
 def lstm_timeline(steps=256):

@@ -92,12 +92,22 @@ int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, in
  */
 int b200_debug_tmem_probe(void* out, void* stream);
 
+/* Number of 8-CTA clusters of the tcgen05 recurrent kernel the current device can hold at once (-1 on error). */
+int b200_debug_lstm_max_clusters(void);
+
 /*
  * Timing aid: after a b200_lstm_rec_fwd launched with B200_LSTM_DEBUG=3 in the environment, copies the SM-clock
  * stamps CTA 0 recorded for its first steps ([step][8] int64, HOST buffer; see lstm_rec_tc.cu).  Returns the
  * number of steps copied (<= 256) or a negative error.
  */
 int b200_debug_lstm_timeline(long long* host_out, int max_steps);
+
+/*
+ * Timing aid: `iters` tcgen05.mma (M=128, N=n, K=16, fp16) round-robin over `chains` independent accumulators, A from
+ * tensor memory (ts_mode=1) or shared memory (0), on `blocks` CTAs; out (device, 3 x int64): issue cycles,
+ * issue-to-completion cycles, nanoseconds.
+ */
+int b200_debug_mma_bench(int ts_mode, int n, int iters, int chains, int blocks, void* out, void* stream);
 
 /* Bytes of scratch b200_crf_decode needs for n chunks of t frames. */
 size_t b200_crf_decode_workspace_bytes(int n, int t, int state_len);
