@@ -7,15 +7,16 @@
 //   * W_hh slice lives in TENSOR MEMORY for the whole kernel as the UMMA A operand: two 128-lane blocks
 //     (rows 0..127 and rows 64..191; fp16 pairs per 32-bit column => 192 columns each).  The tensor core re-reads
 //     all of it every step, which shared memory (128 B/clk) could not feed at N = 32.
-//   * h_{t-1} tile [32 chunks x 384] sits in shared memory, K-major SWIZZLE_128B, as the UMMA B operand
-//     (double buffered by step parity).
+//   * h_{t-1} tile [32 chunks x 384] sits in shared memory as the UMMA B operand, K-major WITHOUT swizzle:
+//     [48 k-chunks of 8 units][32 chunks][16 B], so the 8 units x 32 chunks one warp produces are 512 contiguous
+//     bytes of every peer's tile (double buffered by step parity).
 //   * per step one thread issues 48 tcgen05.mma (M=128, N=32, K=16) -> gate pre-activations in TMEM (64 columns);
 //     six epilogue warps pull them with tcgen05.ld.16x256b -- the mma-accumulator fragment, so with rows ordered
 //     [8 units x (i,f,g,o)] one thread holds all four gates of a (unit, chunk) -- add the prefetched input
-//     projection, update (c, h) in registers, and push the new h slice as 16-byte chunks straight into the h tile
-//     of all 8 CTAs of the cluster (st.async: the store itself completes transaction bytes on the destination's
-//     mbarrier, so there is no fence and no arrive on the sender) and into Y[t].  No __threadfence, no cluster
-//     barrier, no L2 round trip on the recurrence.
+//     projection, update (c, h) in registers, stage the new h block in shared memory and push it into the h tile
+//     of all 8 CTAs of the cluster with one bulk copy per peer (cp.async.bulk shared::cta -> shared::cluster; the copy
+//     completes transaction bytes on the destination's mbarrier, so there is no fence, no arrive and no per-lane
+//     remote store on the sender), and write it to Y[t].  No __threadfence, no cluster barrier, no L2 round trip.
 //
 // Packed operands are the same as for the mma.sync kernel (lstm_rec.cu): whh [CS][UPC/8][gate][8][H],
 // gx [T][N][CS][UPC/8][8][gate], y [T][N][H].
@@ -32,10 +33,11 @@ constexpr int UPC = H / CS;        // 48 units per CTA
 constexpr int ROWS = 4 * UPC;      // 192 gate rows per CTA
 constexpr int KB = H / 64;         // 6 k-blocks of 64
 constexpr int NEPI = ROWS / 32;    // 6 epilogue warps, one 32-row block each
-constexpr int THREADS = 256;
+constexpr int THREADS = 288;       // 8 epilogue warps + the MMA warp
+constexpr int MMA_WARP = 8;
 constexpr uint32_t HTILE = KB * NB * 128;          // 24576 B
 constexpr uint32_t COL_A1 = 0, COL_A2 = 192, COL_D1 = 384, COL_D2 = 416, TMEM_COLS = 512;
-constexpr uint32_t OFF_H = 0, OFF_STAGE = 2 * HTILE, OFF_BARS = OFF_STAGE + NEPI * NB * 16;
+constexpr uint32_t OFF_H = 0, OFF_STAGE = 2 * HTILE, OFF_BARS = OFF_STAGE + 2 * 8 * NB * 16;  // stage: [parity][warp]
 constexpr uint32_t SMEM_USED = OFF_BARS + 64 + 1024;
 // the kernel owns all 512 TMEM columns: ask for more than half of the SM's shared memory so that two CTAs can
 // never be co-resident (a second tcgen05.alloc on the same SM would spin forever)
@@ -49,6 +51,134 @@ __device__ long long g_timeline[TL_STEPS][8];
 
 // VARIANT is a timing-experiment knob (B200_LSTM_DEBUG): 0 = product; 1 = all eight copies of the h chunk go to the
 // CTA's own tile (no inter-SM traffic; wrong results); 2 = cell update replaced by a sum (no SFU work; wrong results).
+// sigma(i), sigma(f), tanh(g), sigma(o) from four ex2 and ONE reciprocal (batch inversion); the exponent arguments are
+// clamped so the product of the four denominators stays finite (sigma(-20.8) = 9e-10: the clamp is invisible in fp16).
+__device__ __forceinline__ void gate_activations(float ai, float af, float ag, float ao, float& si, float& sf, float& tg,
+                                                 float& so) {
+    constexpr float L = 1.4426950408889634f, CLAMP = 30.0f;
+    const float di = 1.0f + exp2f(fminf(-L * ai, CLAMP));
+    const float df = 1.0f + exp2f(fminf(-L * af, CLAMP));
+    const float dg = 1.0f + exp2f(fminf(-2.0f * L * ag, CLAMP));
+    const float dO = 1.0f + exp2f(fminf(-L * ao, CLAMP));
+    const float pif = di * df, pgo = dg * dO;
+    const float r = rcp_approx(pif * pgo);
+    const float rif = r * pgo, rgo = r * pif;
+    si = rif * df;
+    sf = rif * di;
+    tg = fmaf(2.0f, rgo * dO, -1.0f);
+    so = rgo * dg;
+}
+
+// One epilogue warp: row block `blk` (8 hidden units x 4 gates = 32 TMEM lanes at lane quarter `quarter`, accumulator
+// columns [dcol + col0, dcol + col0 + 8*NJ)), i.e. chunks col0 .. col0 + 8*NJ - 1 of the cluster's batch tile.
+template <int NJ, int VARIANT>
+__device__ __forceinline__ void epilogue_warp(const __half* __restrict__ gx, __half* __restrict__ y, int T, int N, int reverse,
+                                              int n0, uint32_t rank, int blk, int quarter, uint32_t dcol, int col0,
+                                              uint32_t tmem_base, uint32_t base, unsigned char* gbase, uint32_t bar_dfull,
+                                              uint32_t bar_hfull0, int warp, int lane) {
+    constexpr int NC = 8 * NJ;  // chunks handled by this warp
+    const int r = lane >> 2, q = lane & 3;
+    const size_t gx_col = (size_t)rank * ROWS + (size_t)blk * 32 + r * 4;
+    const uint32_t stage_off = OFF_STAGE + (uint32_t)warp * NB * 16;                     // + parity * 8*NB*16
+    const int u0 = (int)rank * UPC + blk * 8;                                            // first unit of this block
+    const int my_chunk = col0 + (lane & (NC - 1));                                       // chunk this lane writes to Y
+    // destination inside a peer's h tile: k-chunk (u0/8), rows col0.. : NC*16 contiguous bytes
+    const uint32_t dst_off = OFF_H + (uint32_t)(u0 >> 3) * (NB * 16) + (uint32_t)col0 * 16;
+    // lane d < CS ships this warp's block to peer d (mapa is affine in the offset: window(d) + offset)
+    const uint32_t peer_shift = mapa(base, VARIANT == 1 ? rank : (uint32_t)(lane & (CS - 1))) - base;
+    float c_state[NJ][2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) c_state[j][0] = c_state[j][1] = 0.f;
+
+    // input pre-activations are prefetched one step ahead: they never sit on the recurrence's critical path
+    auto load_gx = [&](int step, uint2 (&dst)[NJ][2]) {
+        const int t = reverse ? (T - 1 - step) : step;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = n0 + col0 + 8 * j + 2 * q + e;
+                dst[j][e] = (n < N) ? __ldg(reinterpret_cast<const uint2*>(gx + ((size_t)t * N + n) * 4 * H + gx_col))
+                                    : make_uint2(0, 0);
+            }
+    };
+    uint2 g[NJ][2], gn[NJ][2];
+    load_gx(0, g);
+
+    for (int step = 0; step < T; ++step) {
+        const int t = reverse ? (T - 1 - step) : step;
+        const int p = step & 1;
+        // staging buffer of this parity: its last readers (bulk copies of step-2) are complete, see kernel comment
+        __half* stage = reinterpret_cast<__half*>(gbase + stage_off + p * (8 * NB * 16));
+        if (step + 1 < T) load_gx(step + 1, gn);
+        mbar_wait(bar_dfull, (uint32_t)(step & 1));
+        const bool tl = VARIANT == 3 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7);
+        const int ts = step % TL_STEPS;
+        if (tl && warp == 0) g_timeline[ts][2] = clock64();
+        tc_fence_after();
+        uint32_t a[4 * NJ], b[4 * NJ];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + dcol + col0;
+        if (NJ == 4) {
+            tc_ld_16x256b_x4(taddr, *reinterpret_cast<uint32_t(*)[16]>(a));                     // rows 0..15: gates i, f
+            tc_ld_16x256b_x4(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[16]>(b));       // rows 16..31: gates g, o
+        } else {
+            tc_ld_16x256b_x2(taddr, *reinterpret_cast<uint32_t(*)[8]>(a));
+            tc_ld_16x256b_x2(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[8]>(b));
+        }
+        tc_wait_ld();
+        tc_fence_before();
+        if (tl && warp == 0) g_timeline[ts][3] = clock64();
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const __half2 g01 = *reinterpret_cast<const __half2*>(&g[j][e].x);
+                const __half2 g23 = *reinterpret_cast<const __half2*>(&g[j][e].y);
+                const float ai = __uint_as_float(a[4 * j + e]) + __low2float(g01);
+                const float af = __uint_as_float(a[4 * j + 2 + e]) + __high2float(g01);
+                const float ag = __uint_as_float(b[4 * j + e]) + __low2float(g23);
+                const float ao = __uint_as_float(b[4 * j + 2 + e]) + __high2float(g23);
+                float c, h;
+                if (VARIANT == 2) {
+                    c = 0.25f * (af + ai + ag) + 0.5f * c_state[j][e];
+                    h = 0.1f * (ao + c);
+                } else {
+                    float si, sf, tg, so;
+                    gate_activations(ai, af, ag, ao, si, sf, tg, so);
+                    c = fmaf(sf, c_state[j][e], si * tg);
+                    h = so * tanh_f(c);
+                }
+                c_state[j][e] = c;
+                stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(h);
+            }
+        fence_proxy_async_smem();   // staged block (generic stores) -> visible to the bulk-copy engine
+        __syncwarp();
+        if (tl && warp == 0) g_timeline[ts][4] = clock64();
+        if (step + 1 < T && lane < CS)
+            bulk_copy_to_peer(base + (p ^ 1) * HTILE + dst_off + peer_shift, base + stage_off + p * (8 * NB * 16), NC * 16,
+                              bar_hfull0 + (p ^ 1) * 8 + peer_shift);
+        if (lane < NC) {
+            const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];  // chunk col0+lane: its 8 units
+            const int n = n0 + my_chunk;
+            if (n < N) *reinterpret_cast<uint4*>(y + ((size_t)t * N + n) * H + u0) = chunk;
+        }
+        if (tl) g_timeline[ts][warp == 0 ? 5 : 7] = clock64();
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { g[j][0] = gn[j][0]; g[j][1] = gn[j][1]; }
+        __syncwarp();
+    }
+}
+
+// Staging-buffer reuse: the block staged at step s (parity p) is read asynchronously by 8 bulk copies.  It is
+// overwritten at step s+2, after this CTA has seen its own h tile of step s+2 complete, which needs every peer's
+// epilogue of step s+1, which needs that peer's h tile of step s+1 complete -- i.e. all copies of step s landed.
+//
+// Warp roles (9 warps).  TMEM lanes: D1 holds gate rows 0..127 (row blocks 0-3), D2 rows 64..191 (blocks 2,3 again,
+// then 4,5); a warp can only read the 32-lane quarter (warp % 4).  Work is spread so that every SM sub-partition gets
+// 1.5 row blocks:       quarter 0        quarter 1        quarter 2         quarter 3
+//   warps 0-3 (32 chunks)  block 0 (D1)     block 1 (D1)     block 4 (D2)      block 5 (D2)
+//   warps 4-7 (16 chunks)  block 2 (D2) 0-15  block 3 (D2) 0-15  block 2 (D1) 16-31  block 3 (D1) 16-31
+//   warp 8                 MMA issuer (+ TMEM allocation)
 template <int VARIANT>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(THREADS, 1)
 lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh, __half* __restrict__ y, int T, int N,
@@ -73,7 +203,7 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
         if (T > 1) mbar_expect_tx(bar_hfull1, HTILE);   // filled during step 0
         if (T > 2) mbar_expect_tx(bar_hfull0, HTILE);   // filled during step 1
     }
-    if (warp == 4) tc_alloc(tmem_slot, TMEM_COLS);
+    if (warp == MMA_WARP) tc_alloc(tmem_slot, TMEM_COLS);
     // h_{-1} = 0
     for (int i = tid; i < (int)(HTILE / 16); i += THREADS) reinterpret_cast<uint4*>(gbase + OFF_H)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
@@ -105,9 +235,9 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    cluster_sync_all();  // every CTA's barriers are initialised before anyone arrives remotely
+    cluster_sync_all();  // every CTA's barriers are initialised before any peer's st.async can land
 
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         // ===== MMA issuer: the whole warp walks the steps, one elected lane issues =====
         constexpr uint32_t idesc = tc_idesc_f16(128, NB);
         for (int step = 0; step < T; ++step) {
@@ -126,112 +256,41 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
                 }
                 tc_fence_after();
                 const uint32_t hb = base + OFF_H + p * HTILE;
+                // B tile: [k-chunk][32 rows][16 B]; one K=16 step = two k-chunks = 1024 B
+                const uint64_t bdesc0 = tc_smem_desc_noswz(hb, NB * 16, 128);
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    const uint64_t bdesc = tc_smem_desc_sw128(hb + kb * (NB * 128));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t acol = (uint32_t)(kb * 4 + k) * 8;
-                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                        tc_mma_ts(tmem_base + COL_D1, tmem_base + COL_A1 + acol, bdesc + 2u * k, idesc, acc);
-                        tc_mma_ts(tmem_base + COL_D2, tmem_base + COL_A2 + acol, bdesc + 2u * k, idesc, acc);
-                    }
+                for (int ks = 0; ks < H / 16; ++ks) {
+                    const uint32_t acol = (uint32_t)ks * 8;
+                    const uint32_t acc = ks != 0 ? 1u : 0u;
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(ks * (2 * NB * 16 / 16));
+                    tc_mma_ts(tmem_base + COL_D1, tmem_base + COL_A1 + acol, bdesc, idesc, acc);
+                    tc_mma_ts(tmem_base + COL_D2, tmem_base + COL_A2 + acol, bdesc, idesc, acc);
                 }
                 tc_commit(bar_dfull);
                 if (VARIANT == 3 && blockIdx.x == 0) g_timeline[step % TL_STEPS][1] = clock64();
             }
             __syncwarp();
         }
-    } else if (warp != 5) {
-        // ===== epilogue warps: warp 0..3 -> row blocks 0..3 (accumulator D1), warps 6,7 -> blocks 4,5 (D2) =====
-        const int blk = warp < 4 ? warp : warp - 2;
+    } else {
         const int quarter = warp & 3;
-        const uint32_t dcol = warp < 4 ? COL_D1 : COL_D2;
-        const int r = lane >> 2, q = lane & 3;
-        const size_t gx_col = (size_t)rank * ROWS + (size_t)blk * 32 + r * 4;
-        __half* stage = reinterpret_cast<__half*>(gbase + OFF_STAGE) + blk * NB * 8;  // [32 chunks][8 units]
-        const int u0 = (int)rank * UPC + blk * 8;                                       // first unit of this block
-        const uint32_t dst_off = (uint32_t)(u0 >> 6) * (NB * 128) + sw128_offset(lane, (u0 & 63) >> 3);
-        float c_state[4][2];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) c_state[j][0] = c_state[j][1] = 0.f;
-
-        // input pre-activations are prefetched one step ahead: they never sit on the recurrence's critical path
-        auto load_gx = [&](int step, uint2 (&dst)[4][2]) {
-            const int t = reverse ? (T - 1 - step) : step;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int n = n0 + 8 * j + 2 * q + e;
-                    dst[j][e] = (n < N) ? __ldg(reinterpret_cast<const uint2*>(gx + ((size_t)t * N + n) * 4 * H + gx_col))
-                                        : make_uint2(0, 0);
-                }
-        };
-        uint2 g[4][2], gn[4][2];
-        load_gx(0, g);
-
-        for (int step = 0; step < T; ++step) {
-            const int t = reverse ? (T - 1 - step) : step;
-            const int p = step & 1;
-            if (step + 1 < T) load_gx(step + 1, gn);
-            mbar_wait(bar_dfull, (uint32_t)(step & 1));
-            const bool tl = VARIANT == 3 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7);
-            const int ts = step % TL_STEPS;
-            if (tl && warp == 0) g_timeline[ts][2] = clock64();
-            tc_fence_after();
-            uint32_t a[16], b[16];
-            tc_ld_16x256b_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + dcol, a);        // rows 0..15: gates i, f
-            tc_ld_16x256b_x4(tmem_base + ((uint32_t)(quarter * 32 + 16) << 16) + dcol, b);   // rows 16..31: gates g, o
-            tc_wait_ld();
-            tc_fence_before();
-            if (tl && warp == 0) g_timeline[ts][3] = clock64();
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const __half2 g01 = *reinterpret_cast<const __half2*>(&g[j][e].x);
-                    const __half2 g23 = *reinterpret_cast<const __half2*>(&g[j][e].y);
-                    const float ai = __uint_as_float(a[4 * j + e]) + __low2float(g01);
-                    const float af = __uint_as_float(a[4 * j + 2 + e]) + __high2float(g01);
-                    const float ag = __uint_as_float(b[4 * j + e]) + __low2float(g23);
-                    const float ao = __uint_as_float(b[4 * j + 2 + e]) + __high2float(g23);
-                    float c, h;
-                    if (VARIANT == 2) {
-                        c = 0.25f * (af + ai + ag) + 0.5f * c_state[j][e];
-                        h = 0.1f * (ao + c);
-                    } else {
-                        c = sigmoid_f(af) * c_state[j][e] + sigmoid_f(ai) * tanh_f(ag);
-                        h = sigmoid_f(ao) * tanh_f(c);
-                    }
-                    c_state[j][e] = c;
-                    stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(h);
-                }
-            __syncwarp();
-            if (tl && warp == 0) g_timeline[ts][4] = clock64();
-            const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];  // chunk `lane`: its 8 units
-            const int n = n0 + lane;
-            if (step + 1 < T) {
-                const uint32_t dst = base + OFF_H + (p ^ 1) * HTILE + dst_off;
-                const uint32_t bar = (p ^ 1) ? bar_hfull1 : bar_hfull0;
-#pragma unroll
-                for (int d = 0; d < CS; ++d) {
-                    const uint32_t peer = VARIANT == 1 ? rank : (uint32_t)d;
-                    st_async_v4(mapa(dst, peer), chunk, mapa(bar, peer));
-                }
-            }
-            if (n < N) *reinterpret_cast<uint4*>(y + ((size_t)t * N + n) * H + u0) = chunk;
-            if (tl) g_timeline[ts][warp == 0 ? 5 : 7] = clock64();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { g[j][0] = gn[j][0]; g[j][1] = gn[j][1]; }
-            __syncwarp();
+        if (warp < 4) {
+            const int blk = quarter < 2 ? quarter : quarter + 2;              // 0, 1, 4, 5
+            const uint32_t dcol = quarter < 2 ? COL_D1 : COL_D2;
+            epilogue_warp<4, VARIANT>(gx, y, T, N, reverse, n0, rank, blk, quarter, dcol, 0, tmem_base, base, gbase,
+                                      bar_dfull, bar_hfull0, warp, lane);
+        } else {
+            const int blk = 2 + (quarter & 1);                                // 2, 3, 2, 3
+            const uint32_t dcol = quarter < 2 ? COL_D2 : COL_D1;
+            const int col0 = quarter < 2 ? 0 : 16;
+            epilogue_warp<2, VARIANT>(gx, y, T, N, reverse, n0, rank, blk, quarter, dcol, col0, tmem_base, base, gbase,
+                                      bar_dfull, bar_hfull0, warp, lane);
         }
     }
 
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // nobody leaves while peers may still write into this CTA's shared memory
-    if (warp == 4) tc_dealloc(tmem_base, TMEM_COLS);
+    if (warp == MMA_WARP) tc_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---- TMEM layout probe (debug / self-test) ----------------------------------------------------------
@@ -240,19 +299,25 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
 // out[4096 .. 4096 + 128*32): D = A * B^T with A (128 x 16, fp16) taken from TMEM, B (32 x 16) from swizzled smem.
 __global__ void __launch_bounds__(128, 1) tmem_probe_kernel(float* __restrict__ out) {
     __shared__ __align__(1024) unsigned char btile[NB * 128];
+    __shared__ __align__(128) unsigned char btile_ns[4096];          // [k chunk][32 rows][16 B], no swizzle (+ slack)
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
-    if (warp == 0) tc_alloc(smem_u32(&slot), 128);
-    for (int i = tid; i < NB * 128 / 4; i += 128) reinterpret_cast<uint32_t*>(btile)[i] = 0;
+    if (warp == 0) tc_alloc(smem_u32(&slot), 256);
+    for (int i = tid; i < NB * 128 / 4; i += 128) {
+        reinterpret_cast<uint32_t*>(btile)[i] = 0;
+        reinterpret_cast<uint32_t*>(btile_ns)[i] = 0;
+    }
     __syncthreads();
     // B[n][k] = ((n + k) % 5) * 0.5, K-major SW128 rows (only the first 32 B of each 128-B row are used)
     if (tid < NB) {
         __half row[16];
         for (int k = 0; k < 16; ++k) row[k] = __float2half(((tid + k) % 5) * 0.5f);
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 2; ++c) {
             *reinterpret_cast<uint4*>(btile + sw128_offset(tid, c)) = *reinterpret_cast<uint4*>(row + 8 * c);
+            *reinterpret_cast<uint4*>(btile_ns + c * (NB * 16) + tid * 16) = *reinterpret_cast<uint4*>(row + 8 * c);
+        }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -277,6 +342,9 @@ __global__ void __launch_bounds__(128, 1) tmem_probe_kernel(float* __restrict__ 
     tc_fence_after();
     if (tid == 0) {
         tc_mma_ts(tb + 64, tb + 32, tc_smem_desc_sw128(smem_u32(btile)), tc_idesc_f16(128, NB), 0u);
+        // the same product with B in the un-swizzled core-matrix layout: (lbo, sbo) = (K step, row-group step) and swapped
+        tc_mma_ts(tb + 96, tb + 32, tc_smem_desc_noswz(smem_u32(btile_ns), NB * 16, 128), tc_idesc_f16(128, NB), 0u);
+        tc_mma_ts(tb + 128, tb + 32, tc_smem_desc_noswz(smem_u32(btile_ns), 128, NB * 16), tc_idesc_f16(128, NB), 0u);
         tc_commit(smem_u32(&bar));
     }
     {
@@ -296,10 +364,16 @@ __global__ void __launch_bounds__(128, 1) tmem_probe_kernel(float* __restrict__ 
         tc_ld_32x32b_x32(tb + ((uint32_t)(warp * 32) << 16) + 64, d);
         tc_wait_ld();
         for (int c = 0; c < 32; ++c) out[4096 + tid * 32 + c] = __uint_as_float(d[c]);
+        tc_ld_32x32b_x32(tb + ((uint32_t)(warp * 32) << 16) + 96, d);
+        tc_wait_ld();
+        for (int c = 0; c < 32; ++c) out[8192 + tid * 32 + c] = __uint_as_float(d[c]);
+        tc_ld_32x32b_x32(tb + ((uint32_t)(warp * 32) << 16) + 128, d);
+        tc_wait_ld();
+        for (int c = 0; c < 32; ++c) out[12288 + tid * 32 + c] = __uint_as_float(d[c]);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc_dealloc(tb, 128);
+    if (warp == 0) tc_dealloc(tb, 256);
 }
 
 }  // namespace

@@ -90,6 +90,12 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint
                      "r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_bar)
                  : "memory");
 }
+// bulk copy own shared memory -> a peer's shared memory (TMA engine); completes `bytes` on the peer's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t peer_dst, uint32_t local_src, uint32_t bytes, uint32_t peer_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                     "r"(peer_dst), "r"(local_src), "r"(bytes), "r"(peer_bar)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 // make generic-proxy writes (st.shared / st.shared::cluster) visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
@@ -144,6 +150,16 @@ __device__ __forceinline__ uint64_t tc_smem_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
     return d;
 }
+// K-major operand tile WITHOUT swizzle: 8-row x 16-byte core matrices (128 contiguous bytes); `lbo` = byte distance
+// between core matrices adjacent along K, `sbo` = between adjacent 8-row groups.
+__device__ __forceinline__ uint64_t tc_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 // byte offset of (row, 16-byte chunk) inside a K-major SWIZZLE_128B tile whose rows are 128 B
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
     return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
@@ -181,6 +197,11 @@ __device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[1
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }

@@ -135,9 +135,9 @@ def lstm_rec(gx, whh, y, t, n, hidden, reverse):
 
 
 def tmem_probe():
-    """Run the TMEM convention probe; returns a float32 CPU tensor of 8192 values."""
+    """Run the TMEM convention probe; returns a float32 CPU tensor of 16384 values."""
     lib = require()
-    out = torch.zeros(8192, dtype=torch.float32, device="cuda")
+    out = torch.zeros(16384, dtype=torch.float32, device="cuda")
     rc = lib.b200_debug_tmem_probe(_ptr(out), _stream())
     _check(rc, "b200_debug_tmem_probe")
     torch.cuda.synchronize()

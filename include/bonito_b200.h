@@ -87,7 +87,7 @@ int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, in
 
 /*
  * Self-test of the tensor-memory conventions the tcgen05 kernels rely on (fragment layout of
- * tcgen05.ld.16x256b, fp16-pair packing of a TMEM-resident A operand).  out: 8192 floats (device);
+ * tcgen05.ld.16x256b, fp16-pair packing of a TMEM-resident A operand, un-swizzled B tiles).  out: 16384 floats (device);
  * interpreted by tests/test_gpu_kernels.py::test_tmem_conventions.
  */
 int b200_debug_tmem_probe(void* out, void* stream);

@@ -136,12 +136,17 @@ def test_tmem_conventions(native):
     if not np.array_equal(frag, want):
         print("observed fragment of thread 0..7:\n", frag[:8])
     assert np.array_equal(frag, want)
-    d = out[4096:].reshape(128, 32)
+    d = out[4096:8192].reshape(128, 32)
     i, n, k = np.arange(128)[:, None, None], np.arange(32)[None, :, None], np.arange(16)[None, None, :]
     ref = ((((i % 7) + k) * 0.25) * (((n + k) % 5) * 0.5)).sum(-1)
     if not np.allclose(d, ref, atol=1e-3):
         print("observed D[0:4, 0:8]:\n", d[:4, :8], "\nexpected:\n", ref[:4, :8])
     np.testing.assert_allclose(d, ref, atol=1e-3)
+    # un-swizzled K-major B tile: leading byte offset = K direction, stride byte offset = 8-row groups
+    ns_a, ns_b = out[8192:12288].reshape(128, 32), out[12288:].reshape(128, 32)
+    print("no-swizzle (lbo=K, sbo=rows) matches:", np.allclose(ns_a, ref, atol=1e-3),
+          "; swapped matches:", np.allclose(ns_b, ref, atol=1e-3))
+    np.testing.assert_allclose(ns_a, ref, atol=1e-3)
 
 
 @pytest.mark.parametrize("impl", ["tcgen05", "mma"])
