@@ -13,7 +13,7 @@
 // bonito/nn.py:226,235-241 (Conv1d), :366-370 (LSTM W_ih), :283-298 + :59-67 (Linear, Clamp).
 #include <cuda.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -25,77 +25,21 @@ struct TcSmem {
     static constexpr uint32_t kA = BM * BK * 2;         // 16 KB
     static constexpr uint32_t kB = BN * BK * 2;         // 16 / 32 KB
     static constexpr uint32_t kStage = kA + kB;
-    static constexpr uint32_t kBars = STAGES * kStage;  // mbarriers after the ring
-    static constexpr uint32_t kTotal = kBars + 256 + 1024;  // + alignment slack
+    static constexpr uint32_t kEpi = STAGES * kStage;        // 4 epilogue warps x (32 rows x 128 B) transpose buffers
+    static constexpr uint32_t kBars = kEpi + 4 * 4096;       // mbarriers after the buffers
+    static constexpr uint32_t kTotal = kBars + 256 + 1024;   // + alignment slack
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
+// ---- PTX wrappers not shared with the other tcgen05 kernels -----------------------------------
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
             "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
-
-// K-major, 128-byte swizzled operand tile: rows of 64 fp16 (128 B), 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address            bits [0,14)
-    d |= (uint64_t)0 << 16;                        // leading byte offset      bits [16,30) (unused, K-major swizzled)
-    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset       bits [32,46)
-    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-    return d;
+    tc_ld_32x32b_x32(taddr, v);
+    tc_wait_ld();
 }
 
 template <int BN>
@@ -143,7 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -159,7 +103,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // instruction descriptor: D=f32, A=B=f16, both K-major, N at [17,23), M at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int stage = 0, acc = 0;
@@ -171,12 +115,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_smem_desc(base + stage * S::kStage);
-                    const uint64_t bdesc = make_smem_desc(base + stage * S::kStage + S::kA);
+                    const uint64_t adesc = tc_smem_desc_sw128(base + stage * S::kStage);
+                    const uint64_t bdesc = tc_smem_desc_sw128(base + stage * S::kStage + S::kA);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // +32 B per K=16 step inside the 128-B swizzle atom (encoded >> 4)
-                        tc_mma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(empty_bar(stage));  // slot free once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -187,7 +131,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ===== epilogue warps (TMEM lanes 32*(warp%4) .. +31) =====
+        // A lane owns one accumulator row; 64 columns at a time are converted, transposed through a swizzled
+        // 32 x 128 B shared-memory buffer and written so that 8 lanes cover 128 contiguous bytes of one output row
+        // (full 128-byte lines instead of 32 scattered half-sectors per store instruction).
         const int quarter = warp & 3;
+        unsigned char* tbuf = gen_base + S::kEpi + quarter * 4096;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -198,29 +146,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const long long orow = (gm < M) ? map_row(ep.map, gm) : -1;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tc_ld32(taddr + c0, v);
+            for (int c0 = 0; c0 < BN; c0 += 64) {
                 const int gn0 = nb * BN + c0;
-                if (orow >= 0 && gn0 < N) {
-                    __half* dst = C + orow * ldc + gn0;
+                if (gn0 >= N) break;  // warp-uniform
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + c0 + half * 32, v);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        if (gn0 + g * 8 >= N) break;  // N % 8 == 0
+                        const int gn = gn0 + half * 32 + g * 8;
                         __half2 packed[4];
                         uint4 braw = make_uint4(0, 0, 0, 0);
-                        if (ep.bias) braw = __ldg(reinterpret_cast<const uint4*>(ep.bias + gn0 + g * 8));
+                        if (ep.bias && gn < N) braw = __ldg(reinterpret_cast<const uint4*>(ep.bias + gn));
                         const __half2* bh = reinterpret_cast<const __half2*>(&braw);
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
-                            float x0 = __uint_as_float(v[g * 8 + 2 * p]) + __low2float(bh[p]);
-                            float x1 = __uint_as_float(v[g * 8 + 2 * p + 1]) + __high2float(bh[p]);
-                            packed[p] = __floats2half2_rn(apply_act_f16(x0, ep.act, ep.lo, ep.hi),
-                                                          apply_act_f16(x1, ep.act, ep.lo, ep.hi));
+                            const float x0 = __uint_as_float(v[g * 8 + 2 * p]) + __low2float(bh[p]);
+                            const float x1 = __uint_as_float(v[g * 8 + 2 * p + 1]) + __high2float(bh[p]);
+                            if (ep.act == B200_ACT_NONE)
+                                packed[p] = __floats2half2_rn(x0, x1);
+                            else
+                                packed[p] = __floats2half2_rn(apply_act_f16(x0, ep.act, ep.lo, ep.hi),
+                                                              apply_act_f16(x1, ep.act, ep.lo, ep.hi));
                         }
-                        *reinterpret_cast<uint4*>(dst + g * 8) = *reinterpret_cast<uint4*>(packed);
+                        const int chunk = half * 4 + g;
+                        *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) =
+                            *reinterpret_cast<uint4*>(packed);
                     }
                 }
+                __syncwarp();
+                const int chunk = lane & 7;
+                const bool col_ok = gn0 + chunk * 8 < N;  // N % 8 == 0
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 4 * i + (lane >> 3);
+                    const long long r = __shfl_sync(0xffffffffu, orow, row);
+                    const uint4 val = *reinterpret_cast<const uint4*>(tbuf + row * 128 + ((chunk ^ (row & 7)) << 4));
+                    if (r >= 0 && col_ok) *reinterpret_cast<uint4*>(C + r * ldc + gn0 + chunk * 8) = val;
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();

@@ -84,8 +84,10 @@ __device__ __forceinline__ void epilogue_warp(const __half* __restrict__ gx, __h
     const int my_chunk = col0 + (lane & (NC - 1));                                       // chunk this lane writes to Y
     // destination inside a peer's h tile: k-chunk (u0/8), rows col0.. : NC*16 contiguous bytes
     const uint32_t dst_off = OFF_H + (uint32_t)(u0 >> 3) * (NB * 16) + (uint32_t)col0 * 16;
-    // lane d < CS ships this warp's block to peer d (mapa is affine in the offset: window(d) + offset)
-    const uint32_t peer_shift = mapa(base, VARIANT == 1 ? rank : (uint32_t)(lane & (CS - 1))) - base;
+    // shared::cluster window of peer d relative to this CTA's (mapa is affine in the offset)
+    uint32_t peer_shift[CS];
+#pragma unroll
+    for (int d = 0; d < CS; ++d) peer_shift[d] = mapa(base, VARIANT == 1 ? rank : (uint32_t)d) - base;
     float c_state[NJ][2];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) c_state[j][0] = c_state[j][1] = 0.f;
@@ -154,9 +156,12 @@ __device__ __forceinline__ void epilogue_warp(const __half* __restrict__ gx, __h
         fence_proxy_async_smem();   // staged block (generic stores) -> visible to the bulk-copy engine
         __syncwarp();
         if (tl && warp == 0) g_timeline[ts][4] = clock64();
-        if (step + 1 < T && lane < CS)
-            bulk_copy_to_peer(base + (p ^ 1) * HTILE + dst_off + peer_shift, base + stage_off + p * (8 * NB * 16), NC * 16,
-                              bar_hfull0 + (p ^ 1) * 8 + peer_shift);
+        if (step + 1 < T && elect_one_sync()) {   // one lane: eight back-to-back bulk copies, one per peer
+            const uint32_t dst = base + (p ^ 1) * HTILE + dst_off, src = base + stage_off + p * (8 * NB * 16);
+            const uint32_t bar = bar_hfull0 + (p ^ 1) * 8;
+#pragma unroll
+            for (int d = 0; d < CS; ++d) bulk_copy_to_peer(dst + peer_shift[d], src, NC * 16, bar + peer_shift[d]);
+        }
         if (lane < NC) {
             const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];  // chunk col0+lane: its 8 units
             const int n = n0 + my_chunk;

@@ -16,6 +16,14 @@ This is the native swap-in the reference performs in `Model.use_koi`
 HBM layout per batch (hac, N=512, L=9996): stem output 164 MB channels-last with halo rows;
 two [T,N,H] activation buffers (655 MB each); one [T,N,4H] gate pre-activation buffer
 (2.6 GB); scores [N,T,1024] (1.75 GB).  Buffers are cached per input shape.
+
+Tile pipelining.  The recurrent kernel runs one 8-CTA cluster per tile of 32 chunks, and a B200 can hold only 15
+such clusters at once (GPC packing; `b200_debug_lstm_max_clusters`), so a 512-chunk batch launched layer by layer
+needs two waves per layer.  Chunks are independent, so `forward` instead gives every 32-chunk tile its own CUDA
+stream and enqueues conv-GEMM -> 5 x (input GEMM -> recurrent kernel) -> CRF GEMM per tile: tiles drift apart in
+layer, the 15 cluster slots stay full (80 tile-layers in 5.3 instead of 10 rounds) and the GEMMs of one tile run on
+the SMs the clusters leave free while other tiles are inside their recurrences.  Activations are kept tile-major:
+`[tile][T][32][H]`.
 """
 
 import torch
@@ -68,6 +76,26 @@ class _Stage:
         if self.sink is not None:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
+            self.sink.append((self.name, self.start, end))
+        return False
+
+
+class _StreamStage(_Stage):
+    """`_Stage` whose events are recorded on an explicit stream."""
+
+    def __init__(self, name, sink, stream):
+        super().__init__(name, sink)
+        self.stream = stream
+
+    def __enter__(self):
+        if self.sink is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record(self.stream)
+
+    def __exit__(self, *exc):
+        if self.sink is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record(self.stream)
             self.sink.append((self.name, self.start, end))
         return False
 
@@ -173,11 +201,116 @@ class LstmCrfPlan:
             self._bufs[key]["stem"][-tail:].zero_()
         return self._bufs[key]
 
-    def forward(self, x, out=None, gemm_impl=native.GEMM_AUTO, return_features=False, events=None):
+    TILE = 32  # chunks per recurrent cluster
+
+    def _tile_buffers(self, N, L):
+        key = ("tiled", N, L)
+        if key not in self._bufs:
+            self._bufs.clear()
+            T = self.frames(L)
+            need = max(self.pad3 + L, (T - 1) * self.s3 + self.k3)
+            Tp = -(-need // self.s3)
+            Lp = Tp * self.s3
+            dev, f16, H = self.device, torch.float16, self.hidden
+            nt = -(-N // self.TILE)
+            tail = self.k3 * self.c2
+            stem = torch.empty(N * Lp * self.c2 + tail, dtype=f16, device=dev)
+            stem[-tail:].zero_()
+            self._bufs[key] = dict(
+                T=T, Tp=Tp, Lp=Lp, nt=nt, stem=stem,
+                ya=torch.empty(nt, T, self.TILE, H, dtype=f16, device=dev),
+                yb=torch.empty(nt, T, self.TILE, H, dtype=f16, device=dev),
+                gx=torch.empty(nt, T, self.TILE, 4 * H, dtype=f16, device=dev),
+                streams=[torch.cuda.Stream(device=dev) for _ in range(nt)],
+                done=[torch.cuda.Event() for _ in range(nt)],
+                start=torch.cuda.Event(),
+            )
+        return self._bufs[key]
+
+    def forward_tiled(self, x, out=None, gemm_impl=native.GEMM_AUTO, events=None, decode=None):
+        """
+        Tile-pipelined forward (see module docstring): same result as `forward(..., tiled=False)`.
+        `decode=(qscale, qbias)`: also enqueue the CRF decode of every tile on that tile's stream, right behind its
+        CRF GEMM (it then overlaps the recurrences of the other tiles); the results are parked in `DECODE_CACHE` and
+        handed out by `CrfDecoder` when it is asked to decode exactly these scores with exactly these parameters.
+        Off by default: measured 5 % slower end to end (34.9 vs 33.0 ms/step), the decode CTAs land on the SMs of
+        the recurrent clusters and lengthen their per-step critical path.
+        """
+        if x.dim() == 3:
+            x = x[:, 0, :]
+        x = x.to(device=self.device, dtype=torch.float16).contiguous()
+        N, L = x.shape
+        H, TB = self.hidden, self.TILE
+        b = self._tile_buffers(N, L)
+        T, Tp, Lp, nt = b["T"], b["Tp"], b["Lp"], b["nt"]
+        if out is None:
+            out = torch.empty(N, T, self.n_scores, dtype=torch.float16, device=self.device)
+        main = torch.cuda.current_stream()
+        dec = None
+        if decode is not None:
+            ws_tile = native.crf_decode_workspace_bytes(TB, T, self.state_len)
+            if b.get("dec_ws") is None or b["dec_ws"].numel() < ws_tile * nt:
+                b["dec_ws"] = torch.empty(ws_tile * nt, dtype=torch.uint8, device=self.device)
+            dec = [torch.empty(N, T, dtype=torch.uint8, device=self.device) for _ in range(3)]  # moves, seq, qual
+
+        with _Stage("conv_stem", events):
+            native.conv_stem(x, self.w1, self.b1, self.act1, self.w2, self.b2, self.act2, b["stem"], Lp, self.pad3)
+        b["start"].record(main)
+        tiles = []
+        for i in range(nt):
+            n0 = i * TB
+            nb = min(TB, N - n0)
+            st = b["streams"][i]
+            st.wait_event(b["start"])
+            tiles.append((i, n0, nb, st))
+
+        def staged(name, st):
+            return _StreamStage(name, events, st)
+
+        # breadth-first enqueue so that every stream has work from the start
+        for i, n0, nb, st in tiles:
+            with staged("conv_gemm", st):   # rows r = i_chunk*Tp + t of this tile -> ya[tile][t][i_chunk]
+                native.gemm(b["stem"][n0 * Lp * self.c2:], self.s3 * self.c2, self.w3, self.b3, b["ya"][i], H, nb * Tp, H,
+                            self.k3 * self.c2, act=self.act3, rows_inner=Tp, valid_inner=T, stride_inner=nb,
+                            stride_outer=1, impl=gemm_impl, stream=st)
+        cur, nxt = b["ya"], b["yb"]
+        for layer in self.lstm:
+            for i, n0, nb, st in tiles:
+                with staged("lstm_in_gemm", st):
+                    native.gemm(cur[i], H, layer["wih"], layer["bias"], b["gx"][i], 4 * H, T * nb, 4 * H, H,
+                                impl=gemm_impl, stream=st)
+                with staged("lstm_rec", st):
+                    native.lstm_rec(b["gx"][i], layer["whh"], nxt[i], T, nb, H, layer["reverse"], stream=st)
+            cur, nxt = nxt, cur
+        for i, n0, nb, st in tiles:
+            with staged("crf_gemm", st):    # rows r = t*nb + i_chunk -> out[n0 + i_chunk][t]
+                native.gemm(cur[i], H, self.wl, self.bl, out[n0:], self.n_scores, T * nb, self.n_scores, H,
+                            act=self.act_l, lo=self.lo, hi=self.hi, rows_inner=nb, valid_inner=nb, stride_inner=T,
+                            stride_outer=1, impl=gemm_impl, stream=st)
+            if dec is not None:
+                with staged("crf_decode", st):
+                    native.crf_decode(out[n0:n0 + nb], self.state_len, self.blank_score, decode[0], decode[1],
+                                      b["dec_ws"][i * ws_tile:], dec[0][n0:], dec[1][n0:], dec[2][n0:], stream=st)
+            b["done"][i].record(st)
+        for i in range(nt):
+            main.wait_event(b["done"][i])
+        if dec is not None:
+            DECODE_CACHE.put(out, (self.state_len, self.blank_score, float(decode[0]), float(decode[1])), tuple(dec))
+        return out
+
+    def forward(self, x, out=None, gemm_impl=native.GEMM_AUTO, return_features=False, events=None, tiled=None,
+                decode=None):
         """
         x: [N, 1, L] (or [N, L]) fp16 CUDA -> scores [N, T, C] fp16 (no blank column).
-        `events`: optional list; (stage, start, end) CUDA events on the current stream are appended per kernel.
+        `events`: optional list; (stage, start, end) CUDA events are appended per kernel.
+        `tiled`: run the tile-pipelined schedule (default: whenever the batch has more than one 32-chunk tile).
+        `decode`: see `forward_tiled` (ignored by the single-stream schedule).
         """
+        if tiled is None:
+            tiled = (not return_features) and x.shape[0] > self.TILE
+        if tiled:
+            return self.forward_tiled(x, out=out, gemm_impl=gemm_impl, events=events, decode=decode)
+
         def stage(name):
             return _Stage(name, events)
 
@@ -222,6 +355,33 @@ class LstmCrfPlan:
         return (out, feats) if return_features else out
 
 
+class _DecodeCache:
+    """Decode results the tile-pipelined forward produced ahead of the `beam_search` call that will ask for them."""
+
+    def __init__(self):
+        self._entry = None
+
+    @staticmethod
+    def _version(t):
+        try:
+            return t._version
+        except RuntimeError:  # inference tensors carry no version counter
+            return -1
+
+    def put(self, scores, params, outputs):
+        self._entry = (scores.data_ptr(), tuple(scores.shape), self._version(scores), params, outputs)
+
+    def take(self, scores, params):
+        e, self._entry = self._entry, None
+        if e is not None and e[0] == scores.data_ptr() and e[1] == tuple(scores.shape) \
+                and e[2] == self._version(scores) and e[3] == params:
+            return e[4]
+        return None
+
+
+DECODE_CACHE = _DecodeCache()
+
+
 def compile_lstm_crf(encoder, device):
     return LstmCrfPlan(encoder, device)
 
@@ -236,6 +396,9 @@ class CrfDecoder:
         n, t, c = scores.shape
         if c != 4 ** (state_len + 1):
             raise ValueError(f"scores width {c} does not match state_len {state_len}")
+        cached = DECODE_CACHE.take(scores, (state_len, float(blank_score), float(qscale), float(qbias)))
+        if cached is not None:
+            return cached
         scores = scores.to(torch.float16).contiguous()
         need = native.crf_decode_workspace_bytes(n, t, state_len)
         if self._ws is None or self._ws.numel() < need or self._ws.device != scores.device:

@@ -80,8 +80,9 @@ def _ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
-def _stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(stream=None):
+    """cudaStream_t for the C ABI: an explicit torch stream, or the current one."""
+    return c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
 
 
 def _f16(t, name):
@@ -108,15 +109,15 @@ def conv_stem(x, w1, b1, act1, w2, b2, act2, out, lp, padl):
 
 
 def gemm(a_ptr_tensor, lda, b, bias, c, ldc, m, n, k, act=ACT_NONE, lo=0.0, hi=0.0,
-         rows_inner=None, valid_inner=None, stride_inner=1, stride_outer=0, impl=GEMM_AUTO):
-    """C = act(A B^T + bias); `a_ptr_tensor` only supplies the base pointer (rows may overlap)."""
+         rows_inner=None, valid_inner=None, stride_inner=1, stride_outer=0, impl=GEMM_AUTO, stream=None):
+    """C = act(A B^T + bias); `a_ptr_tensor` / `c` only supply base pointers (rows may overlap / be remapped)."""
     lib = require()
     if rows_inner is None:
         rows_inner, valid_inner = m, m
     with torch.cuda.device(c.device):
         rc = lib.b200_gemm_fwd(_ptr(a_ptr_tensor), lda, _ptr(_f16(b, "b")), _ptr(bias), _ptr(c), ldc, m, n, k,
                                act, float(lo), float(hi), rows_inner, valid_inner, stride_inner, stride_outer,
-                               impl, _stream())
+                               impl, _stream(stream))
     _check(rc, "b200_gemm_fwd")
     return c
 
@@ -125,11 +126,11 @@ def lstm_cluster_size(hidden):
     return load().b200_lstm_cluster_size(hidden)
 
 
-def lstm_rec(gx, whh, y, t, n, hidden, reverse):
+def lstm_rec(gx, whh, y, t, n, hidden, reverse, stream=None):
     lib = require()
     with torch.cuda.device(y.device):
-        rc = lib.b200_lstm_rec_fwd(_ptr(_f16(gx, "gx")), _ptr(_f16(whh, "whh")), _ptr(y), t, n, hidden,
-                                   int(bool(reverse)), _stream())
+        rc = lib.b200_lstm_rec_fwd(_ptr(gx), _ptr(_f16(whh, "whh")), _ptr(y), t, n, hidden,
+                                   int(bool(reverse)), _stream(stream))
     _check(rc, "b200_lstm_rec_fwd")
     return y
 
@@ -167,11 +168,12 @@ def crf_decode_workspace_bytes(n, t, state_len):
     return load().b200_crf_decode_workspace_bytes(n, t, state_len)
 
 
-def crf_decode(scores, state_len, blank_score, qscale, qbias, workspace, moves, sequence, qstring):
+def crf_decode(scores, state_len, blank_score, qscale, qbias, workspace, moves, sequence, qstring, stream=None):
     lib = require()
     n, t, _ = scores.shape
     with torch.cuda.device(scores.device):
-        rc = lib.b200_crf_decode(_ptr(_f16(scores, "scores")), n, t, state_len, float(blank_score), float(qscale),
-                                 float(qbias), _ptr(workspace), _ptr(moves), _ptr(sequence), _ptr(qstring), _stream())
+        rc = lib.b200_crf_decode(_ptr(scores), n, t, state_len, float(blank_score), float(qscale),
+                                 float(qbias), _ptr(workspace), _ptr(moves), _ptr(sequence), _ptr(qstring),
+                                 _stream(stream))
     _check(rc, "b200_crf_decode")
     return moves, sequence, qstring

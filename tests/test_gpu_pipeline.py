@@ -51,6 +51,20 @@ def test_forward_scores_match_oracle(name, n, L):
         assert errs["scores_mean"] <= tol_mean, errs
 
 
+@pytest.mark.parametrize("n", [33, 70, 128])
+def test_tile_pipelined_forward_is_bit_identical(n):
+    """Per-tile streams (the default for batches above 32 chunks) vs the single-stream layer-by-layer schedule."""
+    model, spec, _ = _model("hac", n_lstm=3)
+    x = synth.squiggle(n, 1200, seed=n).half().cuda()
+    plan = model.native_plan("cuda")
+    with torch.inference_mode():
+        a = plan.forward(x, tiled=False).clone()
+        b = plan.forward(x, tiled=True).clone()
+        c = plan.forward(x).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
 def test_gemm_paths_agree_end_to_end():
     from bonito_b200 import native
     model, spec, _ = _model("hac", n_lstm=2)
