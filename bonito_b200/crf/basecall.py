@@ -24,11 +24,21 @@ def stitch_results(results, length, size, overlap, stride, reverse=False):
     return stitch(results, size, overlap, length, stride, reverse=reverse)
 
 
+_PINNED = {}   # (shape) -> [buffers, next index]: cudaHostAlloc costs milliseconds, so staging buffers are reused
+
+
 def _stage_to_device(batch, device):
     """fp16 cast into pinned memory + async H2D (reference: `batch.to(torch.float16).to(device)`)."""
     if torch.device(device).type != "cuda":
         return batch.to(torch.float16).to(device)
-    pinned = torch.empty(batch.shape, dtype=torch.float16, pin_memory=True)
+    key = tuple(batch.shape)
+    if key not in _PINNED:
+        if len(_PINNED) > 8:
+            _PINNED.clear()
+        _PINNED[key] = [[torch.empty(batch.shape, dtype=torch.float16, pin_memory=True) for _ in range(2)], 0]
+    bufs, idx = _PINNED[key]
+    _PINNED[key][1] = idx ^ 1          # two buffers: the copy of batch i may still be in flight while i+1 is cast
+    pinned = bufs[idx]
     pinned.copy_(batch)
     return pinned.to(device, non_blocking=True)
 

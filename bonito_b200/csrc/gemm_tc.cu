@@ -12,6 +12,7 @@
 // the LSTM input projections and the LinearCRFEncoder (+Clamp) -- reference call sites
 // bonito/nn.py:226,235-241 (Conv1d), :366-370 (LSTM W_ih), :283-298 + :59-67 (Linear, Clamp).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -26,7 +27,8 @@ struct TcSmem {
     static constexpr uint32_t kB = BN * BK * 2;         // 16 / 32 KB
     static constexpr uint32_t kStage = kA + kB;
     static constexpr uint32_t kEpi = STAGES * kStage;        // 4 epilogue warps x (32 rows x 128 B) transpose buffers
-    static constexpr uint32_t kBars = kEpi + 4 * 4096;       // mbarriers after the buffers
+    static constexpr uint32_t kBias = kEpi + 4 * 4096;       // 4 x 512 B: the tile's bias slice, one copy per warp
+    static constexpr uint32_t kBars = kBias + 4 * 512;       // mbarriers after the buffers
     static constexpr uint32_t kTotal = kBars + 256 + 1024;   // + alignment slack
 };
 
@@ -40,6 +42,73 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     tc_ld_32x32b_x32(taddr, v);
     tc_wait_ld();
+}
+
+// Epilogue of one 128 x BN accumulator tile by one warp (its 32 TMEM lanes = 32 output rows).  A lane owns one row;
+// 64 columns at a time are converted, transposed through a swizzled 32 x 128 B shared-memory buffer and written so
+// that 8 lanes cover 128 contiguous bytes of one output row (full 128-byte lines instead of 32 scattered half-sectors
+// per store instruction).
+// One warp copies the BN bias values of column block `nb` into its shared-memory slice (zeros when there is no bias).
+template <int BN>
+__device__ __forceinline__ void stage_bias(__half* sbias, const __half* __restrict__ bias, int nb, int N, int lane) {
+    if (lane < BN / 8) {
+        const int gn = nb * BN + lane * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (bias != nullptr && gn < N) v = __ldg(reinterpret_cast<const uint4*>(bias + gn));
+        reinterpret_cast<uint4*>(sbias)[lane] = v;
+    }
+    __syncwarp();
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* tbuf, const __half* sbias,
+                                              __half* __restrict__ C, long long ldc, int M, int N, int mb, int nb,
+                                              int quarter, int lane, const GemmEpilogue& ep) {
+    const int gm = mb * BM + quarter * 32 + lane;
+    const long long orow = (gm < M) ? map_row(ep.map, gm) : -1;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+        const int gn0 = nb * BN + c0;
+        if (gn0 >= N) break;  // warp-uniform
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tc_ld32(taddr + c0 + half * 32, v);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int gn = gn0 + half * 32 + g * 8;
+                __half2 packed[4];
+                // bias slice of this tile, staged in shared memory by stage_bias() (a global load here would expose
+                // its full latency 32 times per tile: it was 40 % of the epilogue's stall samples)
+                const uint4 braw = *reinterpret_cast<const uint4*>(sbias + c0 + half * 32 + g * 8);
+                const __half2* bh = reinterpret_cast<const __half2*>(&braw);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float x0 = __uint_as_float(v[g * 8 + 2 * p]) + __low2float(bh[p]);
+                    const float x1 = __uint_as_float(v[g * 8 + 2 * p + 1]) + __high2float(bh[p]);
+                    if (ep.act == B200_ACT_NONE)
+                        packed[p] = __floats2half2_rn(x0, x1);
+                    else
+                        packed[p] = __floats2half2_rn(apply_act_f16(x0, ep.act, ep.lo, ep.hi),
+                                                      apply_act_f16(x1, ep.act, ep.lo, ep.hi));
+                }
+                const int chunk = half * 4 + g;
+                *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = *reinterpret_cast<uint4*>(packed);
+            }
+        }
+        __syncwarp();
+        const int chunk = lane & 7;
+        const bool col_ok = gn0 + chunk * 8 < N;  // N % 8 == 0
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + (lane >> 3);
+            const long long r = __shfl_sync(0xffffffffu, orow, row);
+            const uint4 val = *reinterpret_cast<const uint4*>(tbuf + row * 128 + ((chunk ^ (row & 7)) << 4));
+            if (r >= 0 && col_ok) *reinterpret_cast<uint4*>(C + r * ldc + gn0 + chunk * 8) = val;
+        }
+        __syncwarp();
+    }
 }
 
 template <int BN>
@@ -131,62 +200,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ===== epilogue warps (TMEM lanes 32*(warp%4) .. +31) =====
-        // A lane owns one accumulator row; 64 columns at a time are converted, transposed through a swizzled
-        // 32 x 128 B shared-memory buffer and written so that 8 lanes cover 128 contiguous bytes of one output row
-        // (full 128-byte lines instead of 32 scattered half-sectors per store instruction).
         const int quarter = warp & 3;
         unsigned char* tbuf = gen_base + S::kEpi + quarter * 4096;
+        __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + quarter * 512);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int mb = tile / n_blocks, nb = tile % n_blocks;
+            stage_bias<BN>(sbias, ep.bias, nb, N, lane);   // before the wait: its latency hides behind the mainloop
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const int gm = mb * BM + quarter * 32 + lane;
-            const long long orow = (gm < M) ? map_row(ep.map, gm) : -1;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 64) {
-                const int gn0 = nb * BN + c0;
-                if (gn0 >= N) break;  // warp-uniform
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tc_ld32(taddr + c0 + half * 32, v);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int gn = gn0 + half * 32 + g * 8;
-                        __half2 packed[4];
-                        uint4 braw = make_uint4(0, 0, 0, 0);
-                        if (ep.bias && gn < N) braw = __ldg(reinterpret_cast<const uint4*>(ep.bias + gn));
-                        const __half2* bh = reinterpret_cast<const __half2*>(&braw);
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const float x0 = __uint_as_float(v[g * 8 + 2 * p]) + __low2float(bh[p]);
-                            const float x1 = __uint_as_float(v[g * 8 + 2 * p + 1]) + __high2float(bh[p]);
-                            if (ep.act == B200_ACT_NONE)
-                                packed[p] = __floats2half2_rn(x0, x1);
-                            else
-                                packed[p] = __floats2half2_rn(apply_act_f16(x0, ep.act, ep.lo, ep.hi),
-                                                              apply_act_f16(x1, ep.act, ep.lo, ep.hi));
-                        }
-                        const int chunk = half * 4 + g;
-                        *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) =
-                            *reinterpret_cast<uint4*>(packed);
-                    }
-                }
-                __syncwarp();
-                const int chunk = lane & 7;
-                const bool col_ok = gn0 + chunk * 8 < N;  // N % 8 == 0
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = 4 * i + (lane >> 3);
-                    const long long r = __shfl_sync(0xffffffffu, orow, row);
-                    const uint4 val = *reinterpret_cast<const uint4*>(tbuf + row * 128 + ((chunk ^ (row & 7)) << 4));
-                    if (r >= 0 && col_ok) *reinterpret_cast<uint4*>(C + r * ldc + gn0 + chunk * 8) = val;
-                }
-                __syncwarp();
-            }
+            epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, lane, ep);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -200,6 +224,132 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base),
                      "r"((uint32_t)(2 * BN)));
     }
+}
+
+// ---- weight-stationary variant ---------------------------------------------------------------------
+// The streaming kernel above re-reads the B tile (BN x K weights, 196 KB at BN=256, K=384) from L2 for every 128 rows of
+// A: 294 KB of L2 traffic per tile made the LSTM input projection L2-bandwidth bound (~5.4 TB/s of L2 reads).  Here a
+// CTA is bound to ONE column block of B, loads it once into shared memory (<= 144 KB) and streams only A tiles through
+// a 3-stage ring: 98 KB of L2 traffic per tile.
+constexpr int WS_STAGES = 3, WS_KB = 6;  // K <= 384
+
+template <int BN>
+struct WsSmem {
+    static constexpr uint32_t kBres = 0;                                  // [WS_KB][BN rows][128 B] SWIZZLE_128B
+    static constexpr uint32_t kRing = WS_KB * BN * 128;                   // WS_STAGES x (128 x 64 fp16)
+    static constexpr uint32_t kEpi = kRing + WS_STAGES * BM * BK * 2;     // 4 x 4 KB transpose buffers
+    static constexpr uint32_t kBias = kEpi + 4 * 4096;                    // 4 x 512 B bias slice copies
+    static constexpr uint32_t kBars = kBias + 4 * 512;
+    static constexpr uint32_t kTotal = kBars + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep) {
+    using S = WsSmem<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + S::kBars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (WS_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * WS_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * WS_STAGES + 2 + s); };
+    const uint32_t bres_bar = bars + 8u * (2 * WS_STAGES + 4);
+    const uint32_t tmem_slot = bars + 8u * (2 * WS_STAGES + 5);
+    unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
+    const int k_blocks = (K + BK - 1) / BK;
+    const int nb = blockIdx.x % n_blocks;                 // this CTA's column block, for its whole life
+    const int mb0 = blockIdx.x / n_blocks, mb_step = gridDim.x / n_blocks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a));
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b));
+        for (int s = 0; s < WS_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);
+        }
+        mbar_init(bres_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tc_alloc(tmem_slot, BN <= 128 ? 256 : 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + S::kBars + 8u * (2 * WS_STAGES + 5));
+
+    if (warp == 0) {
+        // ===== TMA producer: B once, then A tiles =====
+        if (elect_one_sync()) {
+            mbar_expect_tx(bres_bar, (uint32_t)k_blocks * BN * 128);
+            for (int kb = 0; kb < k_blocks; ++kb)
+                tma_load_2d(base + S::kBres + kb * (BN * 128), &map_b, bres_bar, kb * BK, nb * BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mb = mb0; mb < m_blocks; mb += mb_step) {
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), BM * BK * 2);
+                    tma_load_2d(base + S::kRing + stage * (BM * BK * 2), &map_a, full_bar(stage), kb * BK, mb * BM);
+                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one_sync()) {
+            const uint32_t idesc = tc_idesc_f16(BM, BN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            mbar_wait(bres_bar, 0);
+            for (int mb = mb0; mb < m_blocks; mb += mb_step) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = tc_smem_desc_sw128(base + S::kRing + stage * (BM * BK * 2));
+                    const uint64_t bdesc = tc_smem_desc_sw128(base + S::kBres + kb * (BN * 128));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc_mma_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(empty_bar(stage));
+                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int quarter = warp & 3;
+        unsigned char* tbuf = gen_base + S::kEpi + quarter * 4096;
+        __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + quarter * 512);
+        stage_bias<BN>(sbias, ep.bias, nb, N, lane);       // the column block never changes
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int mb = mb0; mb < m_blocks; mb += mb_step) {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, lane, ep);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc_dealloc(tmem_base, BN <= 128 ? 256 : 512);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -255,12 +405,38 @@ int launch_tc(const __half* A, long long lda, const __half* B, __half* C, long l
     return 0;
 }
 
+template <int BN>
+int launch_ws(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
+              const GemmEpilogue& ep, cudaStream_t stream) {
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, A, M, K, lda, BM);
+    if (rc) return rc;
+    rc = make_map(&map_b, B, N, K, K, BN);
+    if (rc) return rc;
+    auto kern = gemm_ws_kernel<BN>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem<BN>::kTotal));
+    int dev = 0, sms = 0;
+    B200_CHECK_CUDA(cudaGetDevice(&dev));
+    B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
+    int per_block = sms / n_blocks;            // CTAs bound to one column block
+    if (per_block > m_blocks) per_block = m_blocks;
+    if (per_block < 1) per_block = 1;
+    kern<<<per_block * n_blocks, THREADS, WsSmem<BN>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
                    const GemmEpilogue& ep, cudaStream_t stream) {
     B200_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0,
                  "gemm_tc: operands must be 16-byte aligned");
+    const char* env = getenv("B200_GEMM_WS");
+    const bool ws_ok = !(env && env[0] == '0') && K <= WS_KB * BK && M >= 4 * BM;
+    if (ws_ok && N % 192 == 0 && N / 192 <= 64) return launch_ws<192>(A, lda, B, C, ldc, M, N, K, ep, stream);
+    if (ws_ok && N % 128 == 0 && N / 128 <= 64) return launch_ws<128>(A, lda, B, C, ldc, M, N, K, ep, stream);
     if (N % 256 == 0) return launch_tc<256>(A, lda, B, C, ldc, M, N, K, ep, stream);
     return launch_tc<128>(A, lda, B, C, ldc, M, N, K, ep, stream);
 }

@@ -57,11 +57,12 @@ def test_gemm_matches_torch(native, impl_name, m, n, k, bias, act):
     assert err <= 4e-3, err  # one fp16 ulp at |x| < 4 is 2e-3
 
 
-@pytest.mark.parametrize("impl_name", ["tcgen05", "mma"])
-def test_gemm_overlapping_rows_and_row_remap(native, impl_name):
-    """The strided-conv view: rows 96 elements apart, 304 wide; output rows remapped (n,t) -> (t,n)."""
+@pytest.mark.parametrize("impl_name,tp,t_valid", [("tcgen05", 40, 37), ("mma", 40, 37), ("tcgen05", 300, 295)])
+def test_gemm_overlapping_rows_and_row_remap(native, impl_name, tp, t_valid):
+    """The strided-conv view: rows 96 elements apart, 304 wide; output rows remapped (n,t) -> (t,n).
+    (tp=300 is large enough for the weight-stationary kernel, tp=40 runs the streaming one.)"""
     impl = native.GEMM_TCGEN05 if impl_name == "tcgen05" else native.GEMM_MMA_SYNC
-    n_chunks, tp, t_valid, h, k, lda = 3, 40, 37, 384, 304, 96
+    n_chunks, h, k, lda = 3, 384, 304, 96
     g = torch.Generator().manual_seed(5)
     flat = _dev(torch.randn(n_chunks * tp * lda + k, generator=g))
     w = _dev(torch.randn(h, k, generator=g) / k ** 0.5)
