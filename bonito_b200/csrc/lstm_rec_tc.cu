@@ -6,13 +6,16 @@
 // hidden units [48*rank, 48*rank+48) = 192 gate rows of W_hh.
 //   * W_hh slice lives in TENSOR MEMORY for the whole kernel as the UMMA A operand: two 128-lane blocks
 //     (rows 0..127 and rows 64..191; fp16 pairs per 32-bit column => 192 columns each).  The tensor core re-reads
-//     all of it every step, which shared memory (128 B/clk) could not feed at N = 32.
-//   * h_{t-1} tile [32 chunks x 384] sits in shared memory as the UMMA B operand, K-major WITHOUT swizzle:
-//     [48 k-chunks of 8 units][32 chunks][16 B], so the 8 units x 32 chunks one warp produces are 512 contiguous
+//     all of it every step; from shared memory that costs twice as long (59 vs 30 cycles per 128x32x16 MMA measured).
+//   * the tile is processed as TWO interleaved sub-tiles of 16 chunks: while the epilogue warps run the cell update and
+//     the exchange of sub-tile A, the tensor core already works on sub-tile B.  The cost of an MMA here is set by the
+//     A-operand read, not by N, so the split is free on the tensor side and hides ~1/3 of the per-step chain.
+//   * h_{t-1} of a sub-tile [16 chunks x 384] sits in shared memory as the UMMA B operand, K-major WITHOUT swizzle:
+//     [48 k-chunks of 8 units][16 chunks][16 B], so the 8 units x 16 chunks one warp produces are 256 contiguous
 //     bytes of every peer's tile (double buffered by step parity).
-//   * per step one thread issues 48 tcgen05.mma (M=128, N=32, K=16) -> gate pre-activations in TMEM (64 columns);
-//     six epilogue warps pull them with tcgen05.ld.16x256b -- the mma-accumulator fragment, so with rows ordered
-//     [8 units x (i,f,g,o)] one thread holds all four gates of a (unit, chunk) -- add the prefetched input
+//   * per (step, sub-tile) one elected thread issues 48 tcgen05.mma (M=128, N=16, K=16) -> gate pre-activations in
+//     TMEM; eight epilogue warps pull them with tcgen05.ld.16x256b -- the mma-accumulator fragment, so with rows
+//     ordered [8 units x (i,f,g,o)] one thread holds all four gates of a (unit, chunk) -- add the prefetched input
 //     projection, update (c, h) in registers, stage the new h block in shared memory and push it into the h tile
 //     of all 8 CTAs of the cluster with one bulk copy per peer (cp.async.bulk shared::cta -> shared::cluster; the copy
 //     completes transaction bytes on the destination's mbarrier, so there is no fence, no arrive and no per-lane
@@ -27,30 +30,31 @@
 namespace {
 
 constexpr int NB = 32;             // chunks per cluster
+constexpr int NS = 2;              // interleaved sub-tiles
+constexpr int SN = NB / NS;        // 16 chunks per sub-tile = N of one MMA
 constexpr int H = 384;
 constexpr int CS = 8;
 constexpr int UPC = H / CS;        // 48 units per CTA
 constexpr int ROWS = 4 * UPC;      // 192 gate rows per CTA
-constexpr int KB = H / 64;         // 6 k-blocks of 64
-constexpr int NEPI = ROWS / 32;    // 6 epilogue warps, one 32-row block each
 constexpr int THREADS = 288;       // 8 epilogue warps + the MMA warp
 constexpr int MMA_WARP = 8;
-constexpr uint32_t HTILE = KB * NB * 128;          // 24576 B
-constexpr uint32_t COL_A1 = 0, COL_A2 = 192, COL_D1 = 384, COL_D2 = 416, TMEM_COLS = 512;
-constexpr uint32_t OFF_H = 0, OFF_STAGE = 2 * HTILE, OFF_BARS = OFF_STAGE + 2 * 8 * NB * 16;  // stage: [parity][warp]
-constexpr uint32_t SMEM_USED = OFF_BARS + 64 + 1024;
+constexpr uint32_t HT = (H / 8) * SN * 16;         // one h tile: 48 k-chunks x 16 chunks x 16 B = 12288 B
+constexpr uint32_t COL_A1 = 0, COL_A2 = 192, COL_D = 384, TMEM_COLS = 512;   // D: [sub][D1|D2] x 16 columns
+constexpr uint32_t STAGE_WARP = SN * 16;           // 256 B per (parity, sub, warp)
+constexpr uint32_t OFF_H = 0;                      // [sub][parity] h tiles
+constexpr uint32_t OFF_STAGE = NS * 2 * HT;        // [parity][sub][warp]
+constexpr uint32_t OFF_BARS = OFF_STAGE + 2 * NS * 8 * STAGE_WARP;
+constexpr uint32_t SMEM_USED = OFF_BARS + 128 + 1024;
 // the kernel owns all 512 TMEM columns: ask for more than half of the SM's shared memory so that two CTAs can
 // never be co-resident (a second tcgen05.alloc on the same SM would spin forever)
 constexpr uint32_t SMEM_BYTES = SMEM_USED > 120 * 1024 ? SMEM_USED : 120 * 1024;
 
-// timeline of CTA 0 (VARIANT 3): per step, SM-clock stamps of
+// timeline of CTA 0 (VARIANT 3), sub-tile 0: per step, SM-clock stamps of
 //   [0] h tile complete (MMA thread)   [1] MMAs issued + committed   [2] accumulator ready (epilogue warp 0)
 //   [3] TMEM loaded   [4] cell update done   [5] h chunk sent        [6] %globaltimer (ns) at [0]     [7] [5] for warp 7
 constexpr int TL_STEPS = 256;
 __device__ long long g_timeline[TL_STEPS][8];
 
-// VARIANT is a timing-experiment knob (B200_LSTM_DEBUG): 0 = product; 1 = all eight copies of the h chunk go to the
-// CTA's own tile (no inter-SM traffic; wrong results); 2 = cell update replaced by a sum (no SFU work; wrong results).
 // sigma(i), sigma(f), tanh(g), sigma(o) from four ex2 and ONE reciprocal (batch inversion); the exponent arguments are
 // clamped so the product of the four denominators stays finite (sigma(-20.8) = 9e-10: the clamp is invisible in fp16).
 __device__ __forceinline__ void gate_activations(float ai, float af, float ag, float ao, float& si, float& sf, float& tg,
@@ -69,37 +73,47 @@ __device__ __forceinline__ void gate_activations(float ai, float af, float ag, f
     so = rgo * dg;
 }
 
-// One epilogue warp: row block `blk` (8 hidden units x 4 gates = 32 TMEM lanes at lane quarter `quarter`, accumulator
-// columns [dcol + col0, dcol + col0 + 8*NJ)), i.e. chunks col0 .. col0 + 8*NJ - 1 of the cluster's batch tile.
+struct RecBars {
+    uint32_t hfull;   // [sub][parity] at hfull + 8*(2*sub + parity)
+    uint32_t dfull;   // [sub] at dfull + 8*sub
+};
+
+// One epilogue warp: row block `blk` (8 hidden units x 4 gates = 32 TMEM lanes at lane quarter `quarter`), chunks
+// col0 .. col0 + 8*NJ - 1 of EACH 16-chunk sub-tile, accumulator `which` (0: rows 0..127, 1: rows 64..191).
+// VARIANT is a timing-experiment knob (B200_LSTM_DEBUG): 0 = product; 1 = all eight copies of the h block go to the
+// CTA's own tile (no inter-SM traffic; wrong results); 2 = cell update replaced by a sum (no SFU work; wrong
+// results); 3 = product + timeline.
 template <int NJ, int VARIANT>
 __device__ __forceinline__ void epilogue_warp(const __half* __restrict__ gx, __half* __restrict__ y, int T, int N, int reverse,
-                                              int n0, uint32_t rank, int blk, int quarter, uint32_t dcol, int col0,
-                                              uint32_t tmem_base, uint32_t base, unsigned char* gbase, uint32_t bar_dfull,
-                                              uint32_t bar_hfull0, int warp, int lane) {
-    constexpr int NC = 8 * NJ;  // chunks handled by this warp
+                                              int n0, uint32_t rank, int blk, int quarter, int which, int col0,
+                                              uint32_t tmem_base, uint32_t base, unsigned char* gbase, RecBars bars,
+                                              int warp, int lane) {
+    constexpr int NC = 8 * NJ;  // chunks of a sub-tile handled by this warp
     const int r = lane >> 2, q = lane & 3;
     const size_t gx_col = (size_t)rank * ROWS + (size_t)blk * 32 + r * 4;
-    const uint32_t stage_off = OFF_STAGE + (uint32_t)warp * NB * 16;                     // + parity * 8*NB*16
     const int u0 = (int)rank * UPC + blk * 8;                                            // first unit of this block
     const int my_chunk = col0 + (lane & (NC - 1));                                       // chunk this lane writes to Y
     // destination inside a peer's h tile: k-chunk (u0/8), rows col0.. : NC*16 contiguous bytes
-    const uint32_t dst_off = OFF_H + (uint32_t)(u0 >> 3) * (NB * 16) + (uint32_t)col0 * 16;
+    const uint32_t dst_off = (uint32_t)(u0 >> 3) * (SN * 16) + (uint32_t)col0 * 16;
     // shared::cluster window of peer d relative to this CTA's (mapa is affine in the offset)
     uint32_t peer_shift[CS];
 #pragma unroll
     for (int d = 0; d < CS; ++d) peer_shift[d] = mapa(base, VARIANT == 1 ? rank : (uint32_t)d) - base;
-    float c_state[NJ][2];
+    float c_state[NS][NJ][2];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) c_state[j][0] = c_state[j][1] = 0.f;
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) c_state[s][j][0] = c_state[s][j][1] = 0.f;
 
-    // input pre-activations are prefetched one step ahead: they never sit on the recurrence's critical path
-    auto load_gx = [&](int step, uint2 (&dst)[NJ][2]) {
+    // input pre-activations are prefetched one (step, sub-tile) item ahead: never on the recurrence's critical path
+    auto load_gx = [&](int item, uint2 (&dst)[NJ][2]) {
+        const int step = item >> 1, sub = item & 1;
         const int t = reverse ? (T - 1 - step) : step;
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int n = n0 + col0 + 8 * j + 2 * q + e;
+                const int n = n0 + sub * SN + col0 + 8 * j + 2 * q + e;
                 dst[j][e] = (n < N) ? __ldg(reinterpret_cast<const uint2*>(gx + ((size_t)t * N + n) * 4 * H + gx_col))
                                     : make_uint2(0, 0);
             }
@@ -110,80 +124,85 @@ __device__ __forceinline__ void epilogue_warp(const __half* __restrict__ gx, __h
     for (int step = 0; step < T; ++step) {
         const int t = reverse ? (T - 1 - step) : step;
         const int p = step & 1;
-        // staging buffer of this parity: its last readers (bulk copies of step-2) are complete, see kernel comment
-        __half* stage = reinterpret_cast<__half*>(gbase + stage_off + p * (8 * NB * 16));
-        if (step + 1 < T) load_gx(step + 1, gn);
-        mbar_wait(bar_dfull, (uint32_t)(step & 1));
-        const bool tl = VARIANT == 3 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7);
-        const int ts = step % TL_STEPS;
-        if (tl && warp == 0) g_timeline[ts][2] = clock64();
-        tc_fence_after();
-        uint32_t a[4 * NJ], b[4 * NJ];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + dcol + col0;
-        if (NJ == 4) {
-            tc_ld_16x256b_x4(taddr, *reinterpret_cast<uint32_t(*)[16]>(a));                     // rows 0..15: gates i, f
-            tc_ld_16x256b_x4(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[16]>(b));       // rows 16..31: gates g, o
-        } else {
-            tc_ld_16x256b_x2(taddr, *reinterpret_cast<uint32_t(*)[8]>(a));
-            tc_ld_16x256b_x2(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[8]>(b));
-        }
-        tc_wait_ld();
-        tc_fence_before();
-        if (tl && warp == 0) g_timeline[ts][3] = clock64();
 #pragma unroll
-        for (int j = 0; j < NJ; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const __half2 g01 = *reinterpret_cast<const __half2*>(&g[j][e].x);
-                const __half2 g23 = *reinterpret_cast<const __half2*>(&g[j][e].y);
-                const float ai = __uint_as_float(a[4 * j + e]) + __low2float(g01);
-                const float af = __uint_as_float(a[4 * j + 2 + e]) + __high2float(g01);
-                const float ag = __uint_as_float(b[4 * j + e]) + __low2float(g23);
-                const float ao = __uint_as_float(b[4 * j + 2 + e]) + __high2float(g23);
-                float c, h;
-                if (VARIANT == 2) {
-                    c = 0.25f * (af + ai + ag) + 0.5f * c_state[j][e];
-                    h = 0.1f * (ao + c);
-                } else {
-                    float si, sf, tg, so;
-                    gate_activations(ai, af, ag, ao, si, sf, tg, so);
-                    c = fmaf(sf, c_state[j][e], si * tg);
-                    h = so * tanh_f(c);
-                }
-                c_state[j][e] = c;
-                stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(h);
+        for (int sub = 0; sub < NS; ++sub) {
+            const int item = step * NS + sub;
+            // staging buffer (parity, sub): its last readers (bulk copies of step-2) are complete, see kernel comment
+            const uint32_t stage_off = OFF_STAGE + (uint32_t)((p * NS + sub) * 8 + warp) * STAGE_WARP;
+            __half* stage = reinterpret_cast<__half*>(gbase + stage_off);
+            if (item + 1 < T * NS) load_gx(item + 1, gn);
+            mbar_wait(bars.dfull + 8 * sub, (uint32_t)(step & 1));
+            const bool tl = VARIANT == 3 && sub == 0 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7);
+            const int ts = step % TL_STEPS;
+            if (tl && warp == 0) g_timeline[ts][2] = clock64();
+            tc_fence_after();
+            uint32_t a[4 * NJ], b[4 * NJ];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + COL_D + sub * 32 + which * 16 + col0;
+            if (NJ == 2) {
+                tc_ld_16x256b_x2(taddr, *reinterpret_cast<uint32_t(*)[8]>(a));                     // rows 0..15: gates i, f
+                tc_ld_16x256b_x2(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[8]>(b));       // rows 16..31: gates g, o
+            } else {
+                tc_ld_16x256b_x1(taddr, *reinterpret_cast<uint32_t(*)[4]>(a));
+                tc_ld_16x256b_x1(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[4]>(b));
             }
-        fence_proxy_async_smem();   // staged block (generic stores) -> visible to the bulk-copy engine
-        __syncwarp();
-        if (tl && warp == 0) g_timeline[ts][4] = clock64();
-        if (step + 1 < T && elect_one_sync()) {   // one lane: eight back-to-back bulk copies, one per peer
-            const uint32_t dst = base + (p ^ 1) * HTILE + dst_off, src = base + stage_off + p * (8 * NB * 16);
-            const uint32_t bar = bar_hfull0 + (p ^ 1) * 8;
+            tc_wait_ld();
+            tc_fence_before();
+            if (tl && warp == 0) g_timeline[ts][3] = clock64();
 #pragma unroll
-            for (int d = 0; d < CS; ++d) bulk_copy_to_peer(dst + peer_shift[d], src, NC * 16, bar + peer_shift[d]);
-        }
-        if (lane < NC) {
-            const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];  // chunk col0+lane: its 8 units
-            const int n = n0 + my_chunk;
-            if (n < N) *reinterpret_cast<uint4*>(y + ((size_t)t * N + n) * H + u0) = chunk;
-        }
-        if (tl) g_timeline[ts][warp == 0 ? 5 : 7] = clock64();
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) { g[j][0] = gn[j][0]; g[j][1] = gn[j][1]; }
-        __syncwarp();
+                for (int e = 0; e < 2; ++e) {
+                    const __half2 g01 = *reinterpret_cast<const __half2*>(&g[j][e].x);
+                    const __half2 g23 = *reinterpret_cast<const __half2*>(&g[j][e].y);
+                    const float ai = __uint_as_float(a[4 * j + e]) + __low2float(g01);
+                    const float af = __uint_as_float(a[4 * j + 2 + e]) + __high2float(g01);
+                    const float ag = __uint_as_float(b[4 * j + e]) + __low2float(g23);
+                    const float ao = __uint_as_float(b[4 * j + 2 + e]) + __high2float(g23);
+                    float c, h;
+                    if (VARIANT == 2) {
+                        c = 0.25f * (af + ai + ag) + 0.5f * c_state[sub][j][e];
+                        h = 0.1f * (ao + c);
+                    } else {
+                        float si, sf, tg, so;
+                        gate_activations(ai, af, ag, ao, si, sf, tg, so);
+                        c = fmaf(sf, c_state[sub][j][e], si * tg);
+                        h = so * tanh_f(c);
+                    }
+                    c_state[sub][j][e] = c;
+                    stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(h);
+                }
+            fence_proxy_async_smem();   // staged block (generic stores) -> visible to the bulk-copy engine
+            __syncwarp();
+            if (tl && warp == 0) g_timeline[ts][4] = clock64();
+            if (step + 1 < T && elect_one_sync()) {   // one lane: eight back-to-back bulk copies, one per peer
+                const uint32_t dst = base + OFF_H + (uint32_t)(sub * 2 + (p ^ 1)) * HT + dst_off, src = base + stage_off;
+                const uint32_t bar = bars.hfull + 8 * (sub * 2 + (p ^ 1));
+#pragma unroll
+                for (int d = 0; d < CS; ++d) bulk_copy_to_peer(dst + peer_shift[d], src, NC * 16, bar + peer_shift[d]);
+            }
+            if (lane < NC) {
+                const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];  // chunk col0+lane: its 8 units
+                const int n = n0 + sub * SN + my_chunk;
+                if (n < N) *reinterpret_cast<uint4*>(y + ((size_t)t * N + n) * H + u0) = chunk;
+            }
+            if (tl) g_timeline[ts][warp == 0 ? 5 : 7] = clock64();
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) { g[j][0] = gn[j][0]; g[j][1] = gn[j][1]; }
+            __syncwarp();
+        }
     }
 }
 
-// Staging-buffer reuse: the block staged at step s (parity p) is read asynchronously by 8 bulk copies.  It is
-// overwritten at step s+2, after this CTA has seen its own h tile of step s+2 complete, which needs every peer's
-// epilogue of step s+1, which needs that peer's h tile of step s+1 complete -- i.e. all copies of step s landed.
+// Staging-buffer reuse: the block staged at step s (parity p, sub-tile u) is read asynchronously by 8 bulk copies.  It
+// is overwritten at step s+2, after this CTA has seen its own h tile (u, s+2) complete, which needs every peer's
+// epilogue of (u, s+1), which needs that peer's h tile (u, s+1) complete -- i.e. all copies of step s landed.
 //
-// Warp roles (9 warps).  TMEM lanes: D1 holds gate rows 0..127 (row blocks 0-3), D2 rows 64..191 (blocks 2,3 again,
-// then 4,5); a warp can only read the 32-lane quarter (warp % 4).  Work is spread so that every SM sub-partition gets
-// 1.5 row blocks:       quarter 0        quarter 1        quarter 2         quarter 3
-//   warps 0-3 (32 chunks)  block 0 (D1)     block 1 (D1)     block 4 (D2)      block 5 (D2)
-//   warps 4-7 (16 chunks)  block 2 (D2) 0-15  block 3 (D2) 0-15  block 2 (D1) 16-31  block 3 (D1) 16-31
-//   warp 8                 MMA issuer (+ TMEM allocation)
+// Warp roles (9 warps).  TMEM lanes: accumulator 0 holds gate rows 0..127 (row blocks 0-3), accumulator 1 rows 64..191
+// (blocks 2,3 again, then 4,5); a warp can only read the 32-lane quarter (warp % 4).  Work is spread so that every SM
+// sub-partition gets 1.5 row blocks:   quarter 0         quarter 1         quarter 2          quarter 3
+//   warps 0-3 (16 chunks/sub-tile)  block 0 (acc 0)    block 1 (acc 0)    block 4 (acc 1)     block 5 (acc 1)
+//   warps 4-7 ( 8 chunks/sub-tile)  block 2 (acc 1) 0-7  block 3 (acc 1) 0-7  block 2 (acc 0) 8-15  block 3 (acc 0) 8-15
+//   warp 8                          MMA issuer (+ TMEM allocation)
 template <int VARIANT>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(THREADS, 1)
 lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh, __half* __restrict__ y, int T, int N,
@@ -191,8 +210,10 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bar_hfull0 = base + OFF_BARS, bar_hfull1 = bar_hfull0 + 8, bar_dfull = bar_hfull0 + 16;
-    const uint32_t tmem_slot = bar_hfull0 + 24;
+    RecBars bars;
+    bars.hfull = base + OFF_BARS;          // 4 barriers
+    bars.dfull = bars.hfull + 8 * 4;       // 2 barriers
+    const uint32_t tmem_slot = bars.dfull + 8 * 2;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_ctarank();
@@ -200,22 +221,23 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
     const int n0 = group * NB;
 
     if (tid == 0) {
-        mbar_init(bar_hfull0, 1);
-        mbar_init(bar_hfull1, 1);
-        mbar_init(bar_dfull, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(bars.hfull + 8 * i, 1);
+        for (int i = 0; i < 2; ++i) mbar_init(bars.dfull + 8 * i, 1);
         mbar_fence_init();
-        // every fill of an h tile is NB*H*2 bytes of st.async traffic from the 8 CTAs of the cluster
-        if (T > 1) mbar_expect_tx(bar_hfull1, HTILE);   // filled during step 0
-        if (T > 2) mbar_expect_tx(bar_hfull0, HTILE);   // filled during step 1
+        // every fill of an h tile is SN*H*2 bytes of bulk-copy traffic from the 8 CTAs of the cluster
+        for (int sub = 0; sub < NS; ++sub) {
+            if (T > 1) mbar_expect_tx(bars.hfull + 8 * (sub * 2 + 1), HT);   // parity 1: filled during step 0
+            if (T > 2) mbar_expect_tx(bars.hfull + 8 * (sub * 2 + 0), HT);   // parity 0: filled during step 1
+        }
     }
     if (warp == MMA_WARP) tc_alloc(tmem_slot, TMEM_COLS);
-    // h_{-1} = 0
-    for (int i = tid; i < (int)(HTILE / 16); i += THREADS) reinterpret_cast<uint4*>(gbase + OFF_H)[i] = make_uint4(0, 0, 0, 0);
+    // h_{-1} = 0 (parity 0 tiles of both sub-tiles; zeroing everything is simplest)
+    for (int i = tid; i < (int)(NS * 2 * HT / 16); i += THREADS) reinterpret_cast<uint4*>(gbase + OFF_H)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 24);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 8 * 6);
 
     // resident weights -> TMEM (lane = gate row, column c = fp16 pair (2c, 2c+1) of that row)
     if (warp < 4) {
@@ -240,55 +262,56 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    cluster_sync_all();  // every CTA's barriers are initialised before any peer's st.async can land
+    cluster_sync_all();  // every CTA's barriers are initialised before any peer's bulk copy can land
 
     if (warp == MMA_WARP) {
-        // ===== MMA issuer: the whole warp walks the steps, one elected lane issues =====
-        constexpr uint32_t idesc = tc_idesc_f16(128, NB);
+        // ===== MMA issuer: the whole warp walks the (step, sub-tile) items, one elected lane issues =====
+        constexpr uint32_t idesc = tc_idesc_f16(128, SN);
         for (int step = 0; step < T; ++step) {
             const int p = step & 1;
-            if (step > 0) mbar_wait(p ? bar_hfull1 : bar_hfull0, (uint32_t)((((step + 1) >> 1) - 1) & 1));
-            if (elect_one_sync()) {
-                if (step > 0) {
-                    if (step + 2 < T) mbar_expect_tx(p ? bar_hfull1 : bar_hfull0, HTILE);  // re-arm for the fill in step+1
-                    fence_proxy_async_smem();
-                }
-                if (VARIANT == 3 && blockIdx.x == 0) {
-                    g_timeline[step % TL_STEPS][0] = clock64();
-                    unsigned long long gt;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-                    g_timeline[step % TL_STEPS][6] = (long long)gt;
-                }
-                tc_fence_after();
-                const uint32_t hb = base + OFF_H + p * HTILE;
-                // B tile: [k-chunk][32 rows][16 B]; one K=16 step = two k-chunks = 1024 B
-                const uint64_t bdesc0 = tc_smem_desc_noswz(hb, NB * 16, 128);
 #pragma unroll
-                for (int ks = 0; ks < H / 16; ++ks) {
-                    const uint32_t acol = (uint32_t)ks * 8;
-                    const uint32_t acc = ks != 0 ? 1u : 0u;
-                    const uint64_t bdesc = bdesc0 + (uint64_t)(ks * (2 * NB * 16 / 16));
-                    tc_mma_ts(tmem_base + COL_D1, tmem_base + COL_A1 + acol, bdesc, idesc, acc);
-                    tc_mma_ts(tmem_base + COL_D2, tmem_base + COL_A2 + acol, bdesc, idesc, acc);
+            for (int sub = 0; sub < NS; ++sub) {
+                const uint32_t hbar = bars.hfull + 8 * (sub * 2 + p);
+                if (step > 0) mbar_wait(hbar, (uint32_t)((((step + 1) >> 1) - 1) & 1));
+                if (elect_one_sync()) {
+                    if (step > 0) {
+                        if (step + 2 < T) mbar_expect_tx(hbar, HT);   // re-arm for the fill during step+1
+                        fence_proxy_async_smem();
+                    }
+                    if (VARIANT == 3 && sub == 0 && blockIdx.x == 0) {
+                        g_timeline[step % TL_STEPS][0] = clock64();
+                        unsigned long long gt;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                        g_timeline[step % TL_STEPS][6] = (long long)gt;
+                    }
+                    tc_fence_after();
+                    // B tile: [k-chunk][16 rows][16 B]; one K=16 step = two k-chunks = 512 B
+                    const uint64_t bdesc0 = tc_smem_desc_noswz(base + OFF_H + (uint32_t)(sub * 2 + p) * HT, SN * 16, 128);
+                    const uint32_t d1 = tmem_base + COL_D + sub * 32, d2 = d1 + 16;
+#pragma unroll
+                    for (int ks = 0; ks < H / 16; ++ks) {
+                        const uint32_t acol = (uint32_t)ks * 8;
+                        const uint32_t acc = ks != 0 ? 1u : 0u;
+                        const uint64_t bdesc = bdesc0 + (uint64_t)(ks * (2 * SN * 16 / 16));
+                        tc_mma_ts(d1, tmem_base + COL_A1 + acol, bdesc, idesc, acc);
+                        tc_mma_ts(d2, tmem_base + COL_A2 + acol, bdesc, idesc, acc);
+                    }
+                    tc_commit(bars.dfull + 8 * sub);
+                    if (VARIANT == 3 && sub == 0 && blockIdx.x == 0) g_timeline[step % TL_STEPS][1] = clock64();
                 }
-                tc_commit(bar_dfull);
-                if (VARIANT == 3 && blockIdx.x == 0) g_timeline[step % TL_STEPS][1] = clock64();
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         const int quarter = warp & 3;
         if (warp < 4) {
             const int blk = quarter < 2 ? quarter : quarter + 2;              // 0, 1, 4, 5
-            const uint32_t dcol = quarter < 2 ? COL_D1 : COL_D2;
-            epilogue_warp<4, VARIANT>(gx, y, T, N, reverse, n0, rank, blk, quarter, dcol, 0, tmem_base, base, gbase,
-                                      bar_dfull, bar_hfull0, warp, lane);
+            epilogue_warp<2, VARIANT>(gx, y, T, N, reverse, n0, rank, blk, quarter, quarter < 2 ? 0 : 1, 0, tmem_base, base,
+                                      gbase, bars, warp, lane);
         } else {
             const int blk = 2 + (quarter & 1);                                // 2, 3, 2, 3
-            const uint32_t dcol = quarter < 2 ? COL_D2 : COL_D1;
-            const int col0 = quarter < 2 ? 0 : 16;
-            epilogue_warp<2, VARIANT>(gx, y, T, N, reverse, n0, rank, blk, quarter, dcol, col0, tmem_base, base, gbase,
-                                      bar_dfull, bar_hfull0, warp, lane);
+            epilogue_warp<1, VARIANT>(gx, y, T, N, reverse, n0, rank, blk, quarter, quarter < 2 ? 1 : 0, quarter < 2 ? 0 : 8,
+                                      tmem_base, base, gbase, bars, warp, lane);
         }
     }
 
