@@ -28,6 +28,11 @@ import sys
 import threading
 import time
 
+# The engine drives one CUDA stream per 32-chunk tile (16 at batch 512).  With the default of 8 hardware work queues,
+# streams that share a queue serialise behind each other's not-yet-dispatched cluster launches; this must be set
+# before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -53,19 +58,26 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -73,17 +85,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for stamp, r in self.rows:
+            if self.t_begin is not None and not (self.t_begin <= stamp <= (self.t_end or stamp) + 0.06):
+                continue   # only samples taken while the timed region ran
             try:
+                pw.append(float(r[2]))
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, flag in zip(names, r[3:7]):
                     if flag.lower().startswith("active"):
@@ -92,6 +107,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(pw) if pw else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -220,13 +236,14 @@ def main():
         torch.cuda.synchronize()
 
     with torch.inference_mode():
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()          # nvidia-smi needs a moment before its first sample: start it before the warm-up
         for _ in range(max(args.warmup, 3)):
             step_resident()
         barrier()
         log("warm-up done")
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler.mark_begin()
         events = []
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_start.record()
@@ -236,6 +253,7 @@ def main():
         host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps
         t_end.record()
         barrier()
+        sampler.mark_end()
         elapsed_ms = t_start.elapsed_time(t_end)
         log(f"resident: {elapsed_ms / args.steps:.2f} ms/step")
         clocks = sampler.stop() if rank == 0 else None
@@ -284,9 +302,15 @@ def main():
         launch_sms = 8 if launches[dominant] > spec["n_lstm"] else min(8 * n_tiles, sms)
         peak_share = peaks["tflops"] * launch_sms / sms
         chip_ach = flops_step[dominant] / (step_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+                traffic = json.load(fh)["lstm_rec"]["bytes"] if N == BATCH else None
+        except Exception:
+            pass
         roof = {"kernel": "lstm_rec_tc_kernel (persistent tcgen05 LSTM layer, one 8-CTA cluster per 32-chunk tile)",
                 "bound": "tensor", "achieved": ach, "peak": peak_share, "unit": "TFLOP/s", "frac": ach / peak_share,
-                "traffic": None,
+                "traffic": traffic, "traffic_algorithmic": 2.0 * T * min(plan.TILE, N) * 5 * H,
                 "peak_source": f"{peaks['source']} sustained bf16 GEMM {peaks['tflops']} TFLOP/s x {launch_sms}/{sms} SMs "
                                "(the share of the chip one launch occupies)",
                 "launch_ms": dur * 1e3, "launches_per_step": launches[dominant],

@@ -56,6 +56,13 @@ int b200_conv_stem_fwd(const void* x, int n, int l, int c1, int k1, const void* 
 int b200_gemm_fwd(const void* a, long long lda, const void* b, const void* bias, void* c, long long ldc, int m,
                   int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
                   long long stride_inner, long long stride_outer, int impl, void* stream) {
+    return b200_gemm_fwd_ex(a, lda, b, bias, c, ldc, m, n, k, act, lo, hi, rows_inner, valid_inner, stride_inner,
+                            stride_outer, impl, 0, stream);
+}
+
+int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bias, void* c, long long ldc, int m,
+                     int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
+                     long long stride_inner, long long stride_outer, int impl, int max_ctas, void* stream) {
     B200_REQUIRE(a && b && c, "gemm: null pointer argument");
     B200_REQUIRE(m >= 0 && n > 0 && k > 0 && rows_inner > 0, "gemm: bad sizes m=%d n=%d k=%d", m, n, k);
     B200_REQUIRE(k % 8 == 0 && lda % 8 == 0 && n % 8 == 0 && ldc % 8 == 0,
@@ -77,7 +84,7 @@ int b200_gemm_fwd(const void* a, long long lda, const void* b, const void* bias,
     if (impl == B200_GEMM_MMA_SYNC)
         return launch_gemm_mma((const __half*)a, lda, (const __half*)b, (__half*)c, ldc, m, n, k, ep,
                                (cudaStream_t)stream);
-    return launch_gemm_tc((const __half*)a, lda, (const __half*)b, (__half*)c, ldc, m, n, k, ep,
+    return launch_gemm_tc((const __half*)a, lda, (const __half*)b, (__half*)c, ldc, m, n, k, ep, max_ctas,
                           (cudaStream_t)stream);
 }
 

@@ -387,7 +387,7 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, 
 
 template <int BN>
 int launch_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
-              const GemmEpilogue& ep, cudaStream_t stream) {
+              const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, A, M, K, lda, BM);
     if (rc) return rc;
@@ -398,6 +398,7 @@ int launch_tc(const __half* A, long long lda, const __half* B, __half* C, long l
     int dev = 0, sms = 0;
     B200_CHECK_CUDA(cudaGetDevice(&dev));
     B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < sms ? tiles : sms;
     kern<<<grid, THREADS, TcSmem<BN>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep);
@@ -407,7 +408,7 @@ int launch_tc(const __half* A, long long lda, const __half* B, __half* C, long l
 
 template <int BN>
 int launch_ws(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
-              const GemmEpilogue& ep, cudaStream_t stream) {
+              const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, A, M, K, lda, BM);
     if (rc) return rc;
@@ -418,6 +419,7 @@ int launch_ws(const __half* A, long long lda, const __half* B, __half* C, long l
     int dev = 0, sms = 0;
     B200_CHECK_CUDA(cudaGetDevice(&dev));
     B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
     int per_block = sms / n_blocks;            // CTAs bound to one column block
     if (per_block > m_blocks) per_block = m_blocks;
@@ -430,13 +432,13 @@ int launch_ws(const __half* A, long long lda, const __half* B, __half* C, long l
 }  // namespace
 
 int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
-                   const GemmEpilogue& ep, cudaStream_t stream) {
+                   const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
     B200_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0,
                  "gemm_tc: operands must be 16-byte aligned");
     const char* env = getenv("B200_GEMM_WS");
     const bool ws_ok = !(env && env[0] == '0') && K <= WS_KB * BK && M >= 4 * BM;
-    if (ws_ok && N % 192 == 0 && N / 192 <= 64) return launch_ws<192>(A, lda, B, C, ldc, M, N, K, ep, stream);
-    if (ws_ok && N % 128 == 0 && N / 128 <= 64) return launch_ws<128>(A, lda, B, C, ldc, M, N, K, ep, stream);
-    if (N % 256 == 0) return launch_tc<256>(A, lda, B, C, ldc, M, N, K, ep, stream);
-    return launch_tc<128>(A, lda, B, C, ldc, M, N, K, ep, stream);
+    if (ws_ok && N % 192 == 0 && N / 192 <= 64) return launch_ws<192>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+    if (ws_ok && N % 128 == 0 && N / 128 <= 64) return launch_ws<128>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+    if (N % 256 == 0) return launch_tc<256>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+    return launch_tc<128>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
 }

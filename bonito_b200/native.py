@@ -26,6 +26,8 @@ SIGNATURES = {
                                    c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b200_gemm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                               c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_void_p]),
+    "b200_gemm_fwd_ex": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                                 c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_void_p]),
     "b200_lstm_cluster_size": (c_int, [c_int]),
     "b200_lstm_rec_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_debug_tmem_probe": (c_int, [c_void_p, c_void_p]),
@@ -109,15 +111,15 @@ def conv_stem(x, w1, b1, act1, w2, b2, act2, out, lp, padl):
 
 
 def gemm(a_ptr_tensor, lda, b, bias, c, ldc, m, n, k, act=ACT_NONE, lo=0.0, hi=0.0,
-         rows_inner=None, valid_inner=None, stride_inner=1, stride_outer=0, impl=GEMM_AUTO, stream=None):
+         rows_inner=None, valid_inner=None, stride_inner=1, stride_outer=0, impl=GEMM_AUTO, stream=None, max_ctas=0):
     """C = act(A B^T + bias); `a_ptr_tensor` / `c` only supply base pointers (rows may overlap / be remapped)."""
     lib = require()
     if rows_inner is None:
         rows_inner, valid_inner = m, m
     with torch.cuda.device(c.device):
-        rc = lib.b200_gemm_fwd(_ptr(a_ptr_tensor), lda, _ptr(_f16(b, "b")), _ptr(bias), _ptr(c), ldc, m, n, k,
-                               act, float(lo), float(hi), rows_inner, valid_inner, stride_inner, stride_outer,
-                               impl, _stream(stream))
+        rc = lib.b200_gemm_fwd_ex(_ptr(a_ptr_tensor), lda, _ptr(_f16(b, "b")), _ptr(bias), _ptr(c), ldc, m, n, k,
+                                  act, float(lo), float(hi), rows_inner, valid_inner, stride_inner, stride_outer,
+                                  impl, int(max_ctas), _stream(stream))
     _check(rc, "b200_gemm_fwd")
     return c
 

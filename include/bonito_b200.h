@@ -67,6 +67,15 @@ int b200_gemm_fwd(const void* a, long long lda, const void* b, const void* bias,
                   long long stride_inner, long long stride_outer, int impl, void* stream);
 
 /*
+ * Same, with a cap on the number of (persistent) CTAs the tcgen05 kernel may occupy (0 = every SM).  The tile-pipelined
+ * engine caps the GEMMs it runs next to resident recurrent clusters, so that they trickle through the free SMs instead
+ * of flooding the machine and holding back the next cluster launch.
+ */
+int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bias, void* c, long long ldc, int m,
+                     int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
+                     long long stride_inner, long long stride_outer, int impl, int max_ctas, void* stream);
+
+/*
  * Cluster size the packed LSTM operands must be laid out for (0: hidden size unsupported).
  * Supported hidden sizes: 96, 128, 256, 384.
  */
