@@ -122,13 +122,17 @@ class SeqdistModel(Module):
     def native_plan(self, device=None):
         from bonito_b200 import native
         from bonito_b200.engine import compile_lstm_crf
+        from bonito_b200.engine_tf import compile_transformer, find_transformer_encoder
         native.require()
         if device is None:
             device = next(self.parameters()).device
         if torch.device(device).type != "cuda":
             raise native.NativeError("the native path was requested (use_koi) but the model is not on a CUDA device")
         if self._plan is None or self._plan.device != torch.device(device):
-            self._plan = compile_lstm_crf(self.encoder, device)
+            if find_transformer_encoder(self.encoder) is not None:
+                self._plan = compile_transformer(self.encoder, device)
+            else:
+                self._plan = compile_lstm_crf(self.encoder, device)
         return self._plan
 
     def invalidate_plan(self):

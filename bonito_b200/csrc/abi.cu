@@ -14,6 +14,13 @@ int launch_conv_stem(const __half* x, int N, int L, int C1, int K1, const __half
 int lstm_rec_cluster_size(int H);
 int launch_lstm_rec(const __half* gx, const __half* whh, __half* y, int T, int N, int H, int reverse,
                     cudaStream_t stream);
+int launch_conv_first(const __half* x, int N, int L, int C, int K, const __half* w, const __half* bias, int act,
+                      __half* out, int Lp, int padl, cudaStream_t stream);
+int launch_rmsnorm_residual(const __half* a, const __half* x, const __half* w, float alpha, float eps, __half* out,
+                            long long M, int D, cudaStream_t stream);
+int launch_swiglu(const __half* h, __half* out, long long M, int F, cudaStream_t stream);
+int launch_attention(const __half* qkv, const __half* cos_sin, __half* out, int N, int T, int NH, int head_dim, int wl,
+                     int wr, cudaStream_t stream);
 bool lstm_rec_tc_supported(int hidden);
 int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
                        cudaStream_t stream);
@@ -86,6 +93,38 @@ int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bi
                                (cudaStream_t)stream);
     return launch_gemm_tc((const __half*)a, lda, (const __half*)b, (__half*)c, ldc, m, n, k, ep, max_ctas,
                           (cudaStream_t)stream);
+}
+
+int b200_conv_first_fwd(const void* x, int n, int l, int c, int k, const void* w, const void* bias, int act, void* out,
+                        int lp, int padl, void* stream) {
+    B200_REQUIRE(x && w && out, "conv_first: null pointer argument");
+    B200_REQUIRE(n >= 0 && l > 0 && lp >= padl + l, "conv_first: bad sizes n=%d l=%d lp=%d padl=%d", n, l, lp, padl);
+    if (n == 0) return 0;
+    return launch_conv_first((const __half*)x, n, l, c, k, (const __half*)w, (const __half*)bias, act, (__half*)out, lp,
+                             padl, (cudaStream_t)stream);
+}
+
+int b200_attention_fwd(const void* qkv, const void* cos_sin, void* out, int n, int t, int heads, int head_dim, int wl,
+                       int wr, void* stream) {
+    B200_REQUIRE(qkv && cos_sin && out, "attention: null pointer argument");
+    B200_REQUIRE(n >= 0 && t >= 0 && heads > 0, "attention: bad sizes n=%d t=%d heads=%d", n, t, heads);
+    if (n == 0 || t == 0) return 0;
+    return launch_attention((const __half*)qkv, (const __half*)cos_sin, (__half*)out, n, t, heads, head_dim, wl, wr,
+                            (cudaStream_t)stream);
+}
+
+int b200_rmsnorm_residual_fwd(const void* a, const void* x, const void* w, float alpha, float eps, void* out,
+                              long long m, int d, void* stream) {
+    B200_REQUIRE(a && x && w && out, "rmsnorm: null pointer argument");
+    if (m <= 0) return 0;
+    return launch_rmsnorm_residual((const __half*)a, (const __half*)x, (const __half*)w, alpha, eps, (__half*)out, m, d,
+                                   (cudaStream_t)stream);
+}
+
+int b200_swiglu_fwd(const void* h, void* out, long long m, int f, void* stream) {
+    B200_REQUIRE(h && out, "swiglu: null pointer argument");
+    if (m <= 0) return 0;
+    return launch_swiglu((const __half*)h, (__half*)out, m, f, (cudaStream_t)stream);
 }
 
 int b200_lstm_cluster_size(int hidden) { return lstm_rec_cluster_size(hidden); }

@@ -60,6 +60,7 @@ __device__ __forceinline__ float apply_act_f16(float v, int act, float lo, float
         case B200_ACT_SWISH: return round_f16(swish_f(v));
         case B200_ACT_TANH: return round_f16(tanh_f(v));
         case B200_ACT_CLAMP: return fminf(fmaxf(v, lo), hi);
+        case B200_ACT_SCALE: return round_f16(v * lo);
         default: return v;
     }
 }

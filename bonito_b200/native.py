@@ -15,7 +15,7 @@ import torch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbonito_b200.so")
 _lib = None
 
-ACT_NONE, ACT_SWISH, ACT_TANH, ACT_CLAMP = 0, 1, 2, 3
+ACT_NONE, ACT_SWISH, ACT_TANH, ACT_CLAMP, ACT_SCALE = 0, 1, 2, 3, 4
 GEMM_AUTO, GEMM_TCGEN05, GEMM_MMA_SYNC = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol declared in include/bonito_b200.h
@@ -28,6 +28,12 @@ SIGNATURES = {
                               c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_void_p]),
     "b200_gemm_fwd_ex": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_void_p]),
+    "b200_conv_first_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                    c_int, c_void_p]),
+    "b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200_rmsnorm_residual_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_longlong, c_int,
+                                          c_void_p]),
+    "b200_swiglu_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "b200_lstm_cluster_size": (c_int, [c_int]),
     "b200_lstm_rec_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_debug_tmem_probe": (c_int, [c_void_p, c_void_p]),
@@ -122,6 +128,40 @@ def gemm(a_ptr_tensor, lda, b, bias, c, ldc, m, n, k, act=ACT_NONE, lo=0.0, hi=0
                                   impl, int(max_ctas), _stream(stream))
     _check(rc, "b200_gemm_fwd")
     return c
+
+
+def conv_first(x, w, bias, act, out, lp, padl, stream=None):
+    """x [N,L] -> out [N,lp,C] channels-last with zero halo (see b200_conv_first_fwd)."""
+    lib = require()
+    n, l = x.shape
+    c, _, k = w.shape
+    rc = lib.b200_conv_first_fwd(_ptr(_f16(x, "x")), n, l, c, k, _ptr(_f16(w, "w")), _ptr(bias), act, _ptr(out), lp, padl,
+                                 _stream(stream))
+    _check(rc, "b200_conv_first_fwd")
+    return out
+
+
+def attention(qkv, cos_sin, out, n, t, heads, head_dim, wl, wr, stream=None):
+    lib = require()
+    rc = lib.b200_attention_fwd(_ptr(_f16(qkv, "qkv")), _ptr(_f16(cos_sin, "cos_sin")), _ptr(out), n, t, heads, head_dim,
+                                wl, wr, _stream(stream))
+    _check(rc, "b200_attention_fwd")
+    return out
+
+
+def rmsnorm_residual(a, x, w, alpha, eps, out, m, d, stream=None):
+    lib = require()
+    rc = lib.b200_rmsnorm_residual_fwd(_ptr(_f16(a, "a")), _ptr(_f16(x, "x")), _ptr(_f16(w, "w")), float(alpha), float(eps),
+                                       _ptr(out), m, d, _stream(stream))
+    _check(rc, "b200_rmsnorm_residual_fwd")
+    return out
+
+
+def swiglu(h, out, m, f, stream=None):
+    lib = require()
+    rc = lib.b200_swiglu_fwd(_ptr(_f16(h, "h")), _ptr(out), m, f, _stream(stream))
+    _check(rc, "b200_swiglu_fwd")
+    return out
 
 
 def lstm_cluster_size(hidden):

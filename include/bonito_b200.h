@@ -32,6 +32,7 @@ extern "C" {
 #define B200_ACT_SWISH 1
 #define B200_ACT_TANH 2
 #define B200_ACT_CLAMP 3 /* clamp(lo, hi), Clamp layer: bonito/nn.py:59-67 */
+#define B200_ACT_SCALE 4 /* multiply by lo, LinearCRFEncoder.scale: bonito/nn.py:288-289 */
 
 #define B200_GEMM_AUTO 0 /* tcgen05 (product path) unless B200_GEMM_IMPL=mma is set in the environment */
 #define B200_GEMM_TCGEN05 1
@@ -93,6 +94,30 @@ int b200_lstm_cluster_size(int hidden);
  */
 int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, int hidden, int reverse,
                       void* stream);
+
+/*
+ * ---- transformer (sup) path: bonito/transformer/model.py ----
+ *
+ * First convolution of a conv stack: x[N][L] -> Conv1d(1->c, k, pad k/2) + act, channels-last with zero halo:
+ * out[n][padl + l][c], `lp` rows per chunk.  The following convolutions run as b200_gemm_fwd over overlapping rows.
+ */
+int b200_conv_first_fwd(const void* x, int n, int l, int c, int k, const void* w, const void* bias, int act, void* out,
+                        int lp, int padl, void* stream);
+
+/*
+ * Rotary embedding (NeoX half rotation, cos_sin [T][64] fp16 = cos[32] | sin[32] per position) + windowed softmax
+ * attention, non-causal: key j is visible to query i iff i - wl <= j <= i + wr (negative = unlimited).
+ * qkv [N][T][3][heads][64] fp16 (packed projection, bonito/transformer/model.py:71) -> out [N][T][heads*64].
+ */
+int b200_attention_fwd(const void* qkv, const void* cos_sin, void* out, int n, int t, int heads, int head_dim, int wl,
+                       int wr, void* stream);
+
+/* out[r] = rmsnorm(a[r] + fp16(alpha * x[r]), eps) * w   for m rows of d elements (DeepNorm post-norm residual). */
+int b200_rmsnorm_residual_fwd(const void* a, const void* x, const void* w, float alpha, float eps, void* out,
+                              long long m, int d, void* stream);
+
+/* h [m][2f] = (y | gate) -> out [m][f] = gate * y / (1 + exp(-gate))   (GatedMlp with SiLU). */
+int b200_swiglu_fwd(const void* h, void* out, long long m, int f, void* stream);
 
 /*
  * Self-test of the tensor-memory conventions the tcgen05 kernels rely on (fragment layout of

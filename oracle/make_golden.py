@@ -8,6 +8,8 @@ The fixtures are committed; the GPU box (no /root/reference) only replays them.
 Contents
   host_logic.npz   chunk / stitch / batchify results of bonito.util on arange signals, CTC_CRF.idx tables,
                    get_stride, conv length table
+  forward_sup.npz  narrow transformer through the reference's bonito.transformer classes (Triton / CUDA-only pieces
+                   replaced by flash-attn's torch reference functions, see oracle/reference_shim.load_transformer)
   forward_fast.npz reference module tree (bonito.nn via from_dict, BatchNorm folded by fuse_bn_) forward in
                    fp32 on CPU: input, every parameter, per-layer features, scores [T,N,C+blanks];
                    + decode_batch strings (reference glue over the oracle's posteriors stand-in)
@@ -115,6 +117,32 @@ def forward_fast(ref):
     print("forward_fast.npz scores", tuple(scores.shape), "strings", [len(s) for s in strings])
 
 
+def forward_sup(ref):
+    """Narrow transformer (d_model 64, 2 heads, 2 layers) through the reference's own transformer package."""
+    tm = reference_shim.load_transformer()
+    spec = synth.sup_spec(depth=2, d_model=64, nhead=2, dim_feedforward=128, state_len=3)
+    spec["convs"] = [(1, 8, 5, 1, 2, "swish"), (8, 8, 5, 1, 2, "swish"), (8, 16, 9, 3, 4, "swish"),
+                     (16, 16, 9, 2, 4, "swish"), (16, 64, 5, 2, 2, "swish")]
+    cfg = synth.sup_config(spec)
+    torch.manual_seed(25)
+    model = tm.Model(cfg)
+    weights = synth.make_sup_weights(spec, seed=9)
+    missing, unexpected = model.load_state_dict(synth.sup_state_dict(spec, weights), strict=False)
+    assert not unexpected and all("rotary" in k or "inv_freq" in k for k in missing), (missing, unexpected)
+    model.eval()
+    x = synth.squiggle(2, 1200, seed=6)
+    with torch.inference_mode():
+        scores = model(x)                                   # [2T', N, C + blanks]
+        conv = model.encoder.conv(x)                        # [N, T', d]
+        layer0 = model.encoder.transformer_encoder[0](conv)
+    out = {"x": x.numpy(), "scores": scores.numpy(), "conv": conv.numpy(), "layer0": layer0.numpy(),
+           "spec": np.array(json.dumps({k: v for k, v in spec.items()})), "stride": np.array(model.stride)}
+    for k, v in weights.items():
+        out["w." + k] = v.numpy().astype(np.float16)
+    np.savez_compressed(os.path.join(OUT, "forward_sup.npz"), **out)
+    print("forward_sup.npz scores", tuple(scores.shape))
+
+
 def get_stride_ok(ref, model):
     return ref.crf_model.get_stride(model.encoder) == 6 and model.stride == 6
 
@@ -124,6 +152,7 @@ def main():
     ref = reference_shim.load()
     host_logic(ref)
     forward_fast(ref)
+    forward_sup(ref)
 
 
 if __name__ == "__main__":

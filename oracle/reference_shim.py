@@ -77,3 +77,49 @@ def load():
     util = importlib.import_module("bonito.util")
     crf_model = importlib.import_module("bonito.crf.model")
     return types.SimpleNamespace(nn=nn, util=util, crf_model=crf_model)
+
+
+def load_transformer():
+    """
+    The reference's transformer package, runnable on the CPU: its module classes are used unchanged; the pieces that
+    only exist as Triton / CUDA kernels are routed to flash-attn's own torch reference functions:
+      * `attn_func` takes its SDPA + sliding_window_mask branch (bonito/transformer/model.py:61-65)
+        (the capability probe at :59 is answered with (7, 0));
+      * RotaryEmbedding.forward -> flash_attn.layers.rotary.apply_rotary_emb_torch with the module's cos/sin cache
+        recipe (fp32 tables cast to the qkv dtype);
+      * RMSNorm.forward -> flash_attn.ops.triton.layer_norm.rms_norm_ref(upcast=True);
+      * GatedMlp.forward -> fc1, chunk, swiglu_fwd formula (flash_attn/ops/activations.py:107-111), fc2.
+    """
+    load()
+    import importlib
+    # flash-attn's Triton modules probe the CUDA device at import time; answer the probes so they import on a CPU box
+    if not torch.cuda.is_available():
+        torch.cuda.current_device = lambda: 0
+        torch.cuda.get_device_properties = lambda *a, **k: types.SimpleNamespace(
+            warp_size=32, multi_processor_count=1, major=7, minor=0, name="cpu-shim")
+    from flash_attn.layers.rotary import apply_rotary_emb_torch
+    from flash_attn.ops.triton.layer_norm import rms_norm_ref
+    torch.cuda.get_device_capability = lambda *a, **k: (7, 0)
+    tm = importlib.import_module("bonito.transformer.model")
+
+    def rotary_forward(self, qkv, seqlen_offset=0, max_seqlen=None):
+        T = qkv.shape[1]
+        inv_freq = 1.0 / (self.base ** (torch.arange(0, self.dim, 2, dtype=torch.float32) / self.dim))
+        freqs = torch.outer(torch.arange(T, dtype=torch.float32), inv_freq)
+        cos, sin = torch.cos(freqs).to(qkv.dtype), torch.sin(freqs).to(qkv.dtype)
+        q = apply_rotary_emb_torch(qkv[:, :, 0], cos, sin)
+        k = apply_rotary_emb_torch(qkv[:, :, 1], cos, sin)
+        return torch.stack([q, k, qkv[:, :, 2]], dim=2)
+
+    def rmsnorm_forward(self, x, residual=None, prenorm=False, residual_in_fp32=False):
+        return rms_norm_ref(x, self.weight, None, residual=residual, eps=self.eps, upcast=True)
+
+    def gated_forward(self, x):
+        y, gate = self.fc1(x).chunk(2, dim=-1)
+        g = gate.float()
+        return self.fc2((g * y.float() / (1.0 + torch.exp(-g))).to(x.dtype))
+
+    tm.RotaryEmbedding.forward = rotary_forward
+    tm.RMSNorm.forward = rmsnorm_forward
+    tm.GatedMlp.forward = gated_forward
+    return tm

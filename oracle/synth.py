@@ -138,3 +138,85 @@ def squiggle(n, length, seed=25, dwell=10.0, noise=0.15):
 def gaussian_signal(n, length, seed=25):
     gen = torch.Generator().manual_seed(seed)
     return torch.randn(n, 1, length, generator=gen)
+
+
+# ---------------------------------------------------------------------------------------------------
+# transformer (sup v5.0) shapes: /root/reference/bonito/models/configs/dna_r10.4.1@v5.0.toml
+# ---------------------------------------------------------------------------------------------------
+
+def sup_spec(depth=18, d_model=512, nhead=8, dim_feedforward=2048, state_len=5):
+    alpha = round((2 * depth) ** 0.25, 7)
+    beta = round((8 * depth) ** (-1 / 4), 7)
+    return dict(
+        name="sup", depth=depth, d_model=d_model, nhead=nhead, dim_feedforward=dim_feedforward, state_len=state_len,
+        convs=[(1, 64, 5, 1, 2, "swish"), (64, 64, 5, 1, 2, "swish"), (64, 128, 9, 3, 4, "swish"),
+               (128, 128, 9, 2, 4, "swish"), (128, d_model, 5, 2, 2, "swish")],
+        alpha=alpha, beta=beta, window=(127, 128), scale=5.0, blank_score=2.0, stride=6,
+    )
+
+
+def sup_config(spec, batchnorm=False, batchsize=32, chunksize=12000, overlap=600):
+    convs = []
+    for cin, cout, k, s, p, act in spec["convs"]:
+        layer = dict(type="convolution", insize=cin, size=cout, bias=True, winlen=k, stride=s, padding=p, activation=act)
+        if batchnorm:
+            layer["norm"] = "batchnorm"
+        convs.append(layer)
+    convs.append(dict(type="permute", dims=[0, 2, 1]))
+    enc = {
+        "type": "namedserial",
+        "conv": {"type": "serial", "sublayers": convs},
+        "transformer_encoder": {"type": "stack", "depth": spec["depth"], "layer": {
+            "type": "transformerencoderlayer", "d_model": spec["d_model"], "nhead": spec["nhead"],
+            "dim_feedforward": spec["dim_feedforward"], "deepnorm_alpha": spec["alpha"], "deepnorm_beta": spec["beta"],
+            "attn_window": list(spec["window"])}},
+        "upsample": {"type": "linearupsample", "d_model": spec["d_model"], "scale_factor": 2},
+        "crf": {"type": "linearcrfencoder", "insize": spec["d_model"], "n_base": 4, "state_len": spec["state_len"],
+                "bias": False, "scale": spec["scale"], "blank_score": spec["blank_score"], "expand_blanks": True,
+                "permute": [1, 0, 2]},
+    }
+    return {
+        "model": {"type": "seqdistmodel", "package": "bonito.transformer",
+                  "seqdist": {"state_len": spec["state_len"], "alphabet": ["N", "A", "C", "G", "T"]}, "encoder": enc},
+        "qscore": {"scale": 1.05, "bias": 1.3},
+        "basecaller": {"batchsize": batchsize, "chunksize": chunksize, "overlap": overlap},
+    }
+
+
+def make_sup_weights(spec, seed=25, conv_gain=1.8, head_gain=0.55, fp16_values=True):
+    """Seeded weights with the reference's initialisation scheme (xavier with the DeepNorm beta gain on the value /
+    output / feed-forward projections: bonito/transformer/model.py:116-123; RMSNorm weights 1), state-dict names
+    relative to `encoder.`."""
+    gen = torch.Generator().manual_seed(seed)
+    d, ff, beta = spec["d_model"], spec["dim_feedforward"], spec["beta"]
+    w = {}
+    for i, (cin, cout, k, _, _, _) in enumerate(spec["convs"]):
+        w[f"conv.{i}.conv.weight"] = torch.randn(cout, cin, k, generator=gen) * (conv_gain / (cin * k) ** 0.5)
+        w[f"conv.{i}.conv.bias"] = torch.randn(cout, generator=gen) * 0.1
+
+    def xavier(rows, cols, gain):
+        return torch.randn(rows, cols, generator=gen) * gain * (2.0 / (rows + cols)) ** 0.5
+
+    for l in range(spec["depth"]):
+        p = f"transformer_encoder.{l}."
+        w[p + "self_attn.Wqkv.weight"] = torch.cat([xavier(2 * d, d, 1.0) * 3.0, xavier(d, d, beta)])
+        w[p + "self_attn.out_proj.weight"] = xavier(d, d, beta)
+        w[p + "self_attn.out_proj.bias"] = torch.randn(d, generator=gen) * 0.02
+        w[p + "ff.fc1.weight"] = xavier(2 * ff, d, beta)
+        w[p + "ff.fc2.weight"] = xavier(d, ff, beta)
+        w[p + "norm1.weight"] = torch.ones(d)
+        w[p + "norm2.weight"] = torch.ones(d)
+    w["upsample.linear.weight"] = xavier(2 * d, d, 1.0)
+    w["upsample.linear.bias"] = torch.randn(2 * d, generator=gen) * 0.02
+    C = 4 ** (spec["state_len"] + 1)
+    w["crf.linear.weight"] = torch.randn(C, d, generator=gen) * (head_gain / d ** 0.5)
+    if fp16_values:
+        w = {k: v.half().float() for k, v in w.items()}
+    return w
+
+
+def sup_state_dict(spec, weights, prefix="encoder."):
+    sd = {prefix + k: v for k, v in weights.items()}
+    for l in range(spec["depth"]):
+        sd[f"{prefix}transformer_encoder.{l}.deepnorm_alpha"] = torch.tensor(spec["alpha"])
+    return sd
