@@ -19,7 +19,7 @@ int launch_conv_first(const __half* x, int N, int L, int C, int K, const __half*
 int launch_rmsnorm_residual(const __half* a, const __half* x, const __half* w, float alpha, float eps, __half* out,
                             long long M, int D, cudaStream_t stream);
 int launch_swiglu(const __half* h, __half* out, long long M, int F, cudaStream_t stream);
-int launch_attention(const __half* qkv, const __half* cos_sin, __half* out, int N, int T, int NH, int head_dim, int wl,
+int launch_attention(__half* qkv, const __half* cos_sin, __half* out, int N, int T, int NH, int head_dim, int wl,
                      int wr, cudaStream_t stream);
 bool lstm_rec_tc_supported(int hidden);
 int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
@@ -104,12 +104,12 @@ int b200_conv_first_fwd(const void* x, int n, int l, int c, int k, const void* w
                              padl, (cudaStream_t)stream);
 }
 
-int b200_attention_fwd(const void* qkv, const void* cos_sin, void* out, int n, int t, int heads, int head_dim, int wl,
+int b200_attention_fwd(void* qkv, const void* cos_sin, void* out, int n, int t, int heads, int head_dim, int wl,
                        int wr, void* stream) {
     B200_REQUIRE(qkv && cos_sin && out, "attention: null pointer argument");
     B200_REQUIRE(n >= 0 && t >= 0 && heads > 0, "attention: bad sizes n=%d t=%d heads=%d", n, t, heads);
     if (n == 0 || t == 0) return 0;
-    return launch_attention((const __half*)qkv, (const __half*)cos_sin, (__half*)out, n, t, heads, head_dim, wl, wr,
+    return launch_attention((__half*)qkv, (const __half*)cos_sin, (__half*)out, n, t, heads, head_dim, wl, wr,
                             (cudaStream_t)stream);
 }
 

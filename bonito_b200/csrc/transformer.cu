@@ -136,7 +136,39 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// load 64 rows x 64 dims of q or k (which = 0/1) or v (2) starting at token t0 into smem [64][LDT], rotary for q/k
+// Rotary embedding applied once, in place, to the q and k parts of the packed projection (the attention kernel then
+// only copies tiles; rotating inside its loader repeated the work for each of the ~5 query tiles that read a key block).
+// One thread per (token, q|k, head, 8-element group of the first half): rotates (x[d], x[d+32]) for 8 d.
+__global__ void __launch_bounds__(256)
+rotary_kernel(__half* __restrict__ qkv, const __half* __restrict__ cs, long long tokens, int T, int NH) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = tokens * 2 * NH * 4;
+    if (i >= total) return;
+    const int grp = (int)(i & 3);
+    const int head = (int)((i >> 2) % NH);
+    const int which = (int)((i / (4LL * NH)) & 1);
+    const long long tok = i / (8LL * NH);
+    const int t = (int)(tok % T);
+    __half* p = qkv + ((tok * 3 + which) * NH + head) * HD + grp * 8;
+    const __half* c = cs + (size_t)t * 64 + grp * 8;
+    uint4 lo = *reinterpret_cast<uint4*>(p), hi = *reinterpret_cast<uint4*>(p + 32);
+    const uint4 cc = *reinterpret_cast<const uint4*>(c), ss = *reinterpret_cast<const uint4*>(c + 32);
+    __half* x1 = reinterpret_cast<__half*>(&lo);
+    __half* x2 = reinterpret_cast<__half*>(&hi);
+    const __half* co = reinterpret_cast<const __half*>(&cc);
+    const __half* si = reinterpret_cast<const __half*>(&ss);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float a = __half2float(x1[e]), b = __half2float(x2[e]), cf = __half2float(co[e]), sf = __half2float(si[e]);
+        x1[e] = __float2half_rn(a * cf - b * sf);
+        x2[e] = __float2half_rn(a * sf + b * cf);
+    }
+    *reinterpret_cast<uint4*>(p) = lo;
+    *reinterpret_cast<uint4*>(p + 32) = hi;
+}
+
+// load 64 rows x 64 dims of q or k (which = 0/1) or v (2) starting at token t0 into smem [64][LDT]; `cs` != nullptr
+// applies the rotary embedding to q / k on the fly (used when the projection has not been rotated in place)
 __device__ __forceinline__ void load_tile(__half (*dst)[LDT], const __half* __restrict__ qkv, const __half* __restrict__ cs,
                                           int n, int T, int NH, int head, int which, int t0, int tid) {
     const int row = tid >> 1, half16 = (tid & 1) * 16;  // dims [half16, half16+16) and the same + 32
@@ -148,7 +180,7 @@ __device__ __forceinline__ void load_tile(__half (*dst)[LDT], const __half* __re
         lo[1] = *reinterpret_cast<const uint4*>(src + half16 + 8);
         hi[0] = *reinterpret_cast<const uint4*>(src + 32 + half16);
         hi[1] = *reinterpret_cast<const uint4*>(src + 32 + half16 + 8);
-        if (which < 2) {
+        if (which < 2 && cs != nullptr) {
             const __half* c = cs + (size_t)t * 64 + half16;   // cos [T][32] then sin at +32
             const __half* x1 = reinterpret_cast<const __half*>(lo);
             const __half* x2 = reinterpret_cast<const __half*>(hi);
@@ -322,14 +354,16 @@ int launch_swiglu(const __half* h, __half* out, long long M, int F, cudaStream_t
     return 0;
 }
 
-int launch_attention(const __half* qkv, const __half* cos_sin, __half* out, int N, int T, int NH, int head_dim, int wl,
+int launch_attention(__half* qkv, const __half* cos_sin, __half* out, int N, int T, int NH, int head_dim, int wl,
                      int wr, cudaStream_t stream) {
     B200_REQUIRE(head_dim == HD, "attention: head_dim %d is not supported (64)", head_dim);
     if (wl < 0) wl = T;
     if (wr < 0) wr = T;
+    const long long tokens = (long long)N * T, work = tokens * 2 * NH * 4;
+    rotary_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(qkv, cos_sin, tokens, T, NH);
     dim3 grid((T + AQ - 1) / AQ, NH, N);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
-    attention_kernel<<<grid, 128, 0, stream>>>(qkv, cos_sin, out, T, NH, wl, wr, scale_log2e);
+    attention_kernel<<<grid, 128, 0, stream>>>(qkv, nullptr, out, T, NH, wl, wr, scale_log2e);
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -108,8 +108,9 @@ int b200_conv_first_fwd(const void* x, int n, int l, int c, int k, const void* w
  * Rotary embedding (NeoX half rotation, cos_sin [T][64] fp16 = cos[32] | sin[32] per position) + windowed softmax
  * attention, non-causal: key j is visible to query i iff i - wl <= j <= i + wr (negative = unlimited).
  * qkv [N][T][3][heads][64] fp16 (packed projection, bonito/transformer/model.py:71) -> out [N][T][heads*64].
+ * The q and k parts of `qkv` are rotated IN PLACE (as flash-attn's RotaryEmbedding does, transformer/model.py:73).
  */
-int b200_attention_fwd(const void* qkv, const void* cos_sin, void* out, int n, int t, int heads, int head_dim, int wl,
+int b200_attention_fwd(void* qkv, const void* cos_sin, void* out, int n, int t, int heads, int head_dim, int wl,
                        int wr, void* stream);
 
 /* out[r] = rmsnorm(a[r] + fp16(alpha * x[r]), eps) * w   for m rows of d elements (DeepNorm post-norm residual). */

@@ -51,6 +51,9 @@ def model_config(spec, batchnorm=False, batchsize=32, chunksize=3996, overlap=49
         "input": {"features": 1},
         "global_norm": {"state_len": spec["state_len"]},
         "qscore": {"scale": 1.05, "bias": 0.2},
+        # picoampere input, standardised with fixed statistics (v4.3+/v5 LSTM configs)
+        "scaling": {"strategy": "pa"},
+        "standardisation": {"standardise": 1, "mean": 93.7, "stdev": 23.5},
         "encoder": {"type": "serial", "sublayers": sub},
         "basecaller": {"batchsize": batchsize, "chunksize": chunksize, "overlap": overlap},
     }

@@ -153,3 +153,33 @@ def test_full_size_properties():
         seq, q, moves = beam_search(s1)
     assert torch.equal(seq[:64], seq[448:]) and int(moves.sum()) > 512 * 300
     assert float((s1.float().abs() >= 5).float().mean()) < 0.05
+
+
+def test_cli_basecaller_end_to_end(tmp_path):
+    """`python -m bonito_b200 basecaller <model dir> <reads dir>` on synthetic .npy reads -> FASTQ on stdout."""
+    import os, subprocess, sys
+    from bonito_b200.crf.basecall import basecall
+    from bonito_b200.nn import fuse_bn_
+    from bonito_b200.reader import Reader
+    from bonito_b200.util import load_model
+    spec = synth.model_spec("fast", n_lstm=3)
+    weights = synth.make_weights(spec, seed=4)
+    mdir = synth.write_model_dir(str(tmp_path / "model"), spec, weights, batchsize=8, chunksize=2000, overlap=120)
+    rdir = tmp_path / "reads"
+    rdir.mkdir()
+    for i, n in enumerate([5000, 1500, 7777]):
+        np.save(rdir / f"read{i}.npy", 93.7 + 23.5 * synth.squiggle(1, n, seed=20 + i)[0, 0].numpy())   # picoamperes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "bonito_b200", "basecaller", mdir, str(rdir), "--no-trim"], cwd=root,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "> samples per second" in out.stderr and "> completed reads: 3" in out.stderr, out.stderr[-1500:]
+    lines = out.stdout.strip().split("\n")
+    records = {lines[i][1:]: (lines[i + 1], lines[i + 3]) for i in range(0, len(lines), 4)}
+    assert sorted(records) == ["read0", "read1", "read2"]
+    model = load_model(mdir, "cuda", use_koi=True).apply(fuse_bn_)
+    reads = Reader(str(rdir)).get_reads(str(rdir), do_trim=False, scaling_strategy=model.config["scaling"],
+                                        norm_params=model.config["standardisation"])
+    p = model.config["basecaller"]
+    for read, res in basecall(model, reads, batchsize=p["batchsize"], chunksize=p["chunksize"], overlap=p["overlap"]):
+        assert records[read.read_id] == (res["sequence"], res["qstring"]) and len(res["sequence"]) > 50
