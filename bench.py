@@ -129,11 +129,12 @@ def build_model(device, rank, world):
     return model, spec, weights, chunksize
 
 
-def cpu_baseline(spec, weights, chunksize, n_chunks=16, threads=None):
+def cpu_baseline(spec, weights, chunksize, n_chunks=32, threads=None):
     from oracle import synth
     from oracle.cpu_reference import CpuReferenceModel
     threads = threads or min(os.cpu_count(), 32)
     torch.set_num_threads(threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     log(f"cpu baseline: {n_chunks} chunks on {threads} threads (host has {os.cpu_count()})")
     ref = CpuReferenceModel(spec, weights)
     x = synth.squiggle(n_chunks, chunksize, seed=25)
@@ -145,7 +146,7 @@ def cpu_baseline(spec, weights, chunksize, n_chunks=16, threads=None):
     return {"value": samples / (tf + td), "unit": "samples/s", "cores": threads, "kind": "port",
             "forward_only": samples / tf,
             "sample": f"{n_chunks} chunks x {chunksize} samples, torch {torch.__version__} fp32 modules as bonito.nn builds "
-                      f"them + numpy posterior-Viterbi decode (forward {tf:.2f}s, decode {td:.2f}s)"}
+                      f"them + OpenMP C posterior-Viterbi decode (forward {tf:.2f}s, decode {td:.2f}s)"}
 
 
 def run_reference(args, rank, world):
@@ -159,8 +160,9 @@ def run_reference(args, rank, world):
     from oracle.cpu_reference import CpuReferenceModel
     threads = min(os.cpu_count(), 32)
     torch.set_num_threads(threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     ref = CpuReferenceModel(spec, weights)
-    n_chunks = 8
+    n_chunks = 32
     x = synth.squiggle(n_chunks, chunksize, seed=25)
     for _ in range(max(args.warmup, 1)):
         ref.forward(x[:2])

@@ -2,7 +2,9 @@
 ORACLE -- TEST INFRASTRUCTURE ONLY.  The reference's PyTorch-CPU execution of the path, rebuilt from torch
 modules exactly as `bonito.nn` builds them (torch.nn.Conv1d / torch.nn.LSTM with flip / torch.nn.Linear / clamp:
 `/root/reference/bonito/nn.py:226,361-370,279-298,66-67`), followed by the oracle's restatement of
-`SeqdistModel.decode_batch` (the reference's basecaller decode is CUDA-only koi, `bonito/crf/basecall.py:36-40`).
+`SeqdistModel.decode_batch` (the reference's basecaller decode is CUDA-only koi, `bonito/crf/basecall.py:36-40`): the
+OpenMP C version (`oracle/csrc/crf_decode_ref.c`, bit-identical to the numpy one on the fixtures) so that the CPU arm is not
+handicapped by numpy overheads.
 
 Used by `bench.py` for the `cpu_baseline` leg and the `--impl reference` arm (the reference itself is Python and
 cannot travel to the GPU box; its sources are never copied).
@@ -13,7 +15,7 @@ import time
 import numpy as np
 import torch
 
-from oracle import crf_oracle
+from oracle import build_ref, crf_oracle
 
 
 class CpuReferenceModel(torch.nn.Module):
@@ -59,14 +61,17 @@ class CpuReferenceModel(torch.nn.Module):
             s = s.clamp(*self.spec["clamp"])
         return s
 
-    def basecall_batch(self, x, decode_slice=4):
-        """forward + decode; returns (moves, seq, qual, t_forward, t_decode)."""
+    def basecall_batch(self, x, decode="c", decode_slice=4):
+        """forward + decode; returns (moves, seq, qual, t_forward, t_decode).  decode: "c" (OpenMP) or "numpy"."""
         t0 = time.perf_counter()
         s = self.forward(x)
         t1 = time.perf_counter()
         ntc = s.permute(1, 0, 2).contiguous().numpy()
-        outs = [crf_oracle.decode_native(ntc[i:i + decode_slice], self.spec["state_len"], self.spec["blank_score"])[:3]
-                for i in range(0, ntc.shape[0], decode_slice)]
+        if decode == "c":
+            moves, seq, qual = build_ref.decode(ntc, self.spec["state_len"], self.spec["blank_score"])
+        else:
+            outs = [crf_oracle.decode_native(ntc[i:i + decode_slice], self.spec["state_len"], self.spec["blank_score"])[:3]
+                    for i in range(0, ntc.shape[0], decode_slice)]
+            moves, seq, qual = (np.concatenate(p) for p in zip(*outs))
         t2 = time.perf_counter()
-        moves, seq, qual = (np.concatenate(p) for p in zip(*outs))
         return moves, seq, qual, t1 - t0, t2 - t1

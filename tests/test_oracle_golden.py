@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import crf_oracle as O
+from oracle import build_ref, crf_oracle as O
 from oracle import synth
 
 
@@ -83,3 +83,22 @@ def test_native_layout_decode_equals_decode_batch(gold):
     assert got == json.loads(str(gold["strings"]))
     assert np.array_equal(moves, (seq != 0).astype(np.uint8)) and np.array_equal(seq != 0, qual != 0)
     assert np.all(mass >= 0) and np.all(mass.sum(-1) <= 1 + 1e-9)
+
+
+def test_c_decode_matches_numpy_oracle(gold):
+    """oracle/csrc/crf_decode_ref.c (the CPU-baseline decode) == crf_oracle.decode_native, incl. qualities, on the golden
+    scores and on seeded random scores of every state length."""
+    s = gold["scores"].reshape(250, 3, 64, 5)
+    scores = np.ascontiguousarray(s[..., 1:].reshape(250, 3, 256).transpose(1, 0, 2))
+    a = build_ref.decode(scores, 3, 2.0, 1.05, 0.2)
+    b = O.decode_native(scores, 3, 2.0, 1.05, 0.2)[:3]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert [r[r != 0].tobytes().decode() for r in a[1]] == json.loads(str(gold["strings"]))
+    g = np.random.default_rng(3)
+    for k, n, t in [(3, 3, 200), (4, 2, 150), (5, 1, 40)]:
+        sc = np.clip(g.normal(size=(n, t, 4 ** (k + 1))) * 1.7, -5, 5).astype(np.float16).astype(np.float32)
+        a = build_ref.decode(sc, k)
+        b = O.decode_native(sc, k)[:3]
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
