@@ -74,6 +74,9 @@ int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bi
     B200_REQUIRE(m >= 0 && n > 0 && k > 0 && rows_inner > 0, "gemm: bad sizes m=%d n=%d k=%d", m, n, k);
     B200_REQUIRE(k % 8 == 0 && lda % 8 == 0 && n % 8 == 0 && ldc % 8 == 0,
                  "gemm: k, lda, n, ldc must be multiples of 8 (k=%d lda=%lld n=%d ldc=%lld)", k, lda, n, ldc);
+    if (act == B200_ACT_SWIGLU)
+        B200_REQUIRE(n % 64 == 0 && !bias && impl != B200_GEMM_MMA_SYNC,
+                     "gemm: the fused SwiGLU epilogue needs n %% 64 == 0, no bias and the tcgen05 path (n=%d)", n);
     if (m == 0) return 0;
     GemmEpilogue ep;
     ep.bias = (const __half*)bias;
@@ -86,7 +89,7 @@ int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bi
     ep.map.stride_outer = stride_outer;
     if (impl == B200_GEMM_AUTO) {
         const char* env = getenv("B200_GEMM_IMPL");
-        impl = (env && strcmp(env, "mma") == 0) ? B200_GEMM_MMA_SYNC : B200_GEMM_TCGEN05;
+        impl = (env && strcmp(env, "mma") == 0 && act != B200_ACT_SWIGLU) ? B200_GEMM_MMA_SYNC : B200_GEMM_TCGEN05;
     }
     if (impl == B200_GEMM_MMA_SYNC)
         return launch_gemm_mma((const __half*)a, lda, (const __half*)b, (__half*)c, ldc, m, n, k, ep,

@@ -5,9 +5,10 @@
 //              into a 4-stage shared-memory ring, completion on mbarriers
 //   warp 1     MMA issuer: one lane issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16),
 //              accumulating in TMEM; tcgen05.commit releases ring slots / publishes accumulators
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias -> fp16 rounding -> activation ->
-//              row-remapped 16-byte stores.  TMEM holds two accumulator stages (2 x BN columns) so the
-//              epilogue of tile i overlaps the mainloop of tile i+1 (K is only 304..384 here).
+//   warps 2-9  epilogue, two warps per 32-lane TMEM quarter taking alternate 32-column blocks: tcgen05.ld (32 lanes x
+//              32 columns) -> bias -> fp16 rounding -> activation (or the fused SwiGLU product) -> row-remapped
+//              16-byte stores.  TMEM holds two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps
+//              the mainloop of tile i+1 (K is only 304..512 here, so the epilogue is as long as the mainloop).
 // Used for: the strided conv of the encoder (overlapping-row view of the conv-stem output, lda < K),
 // the LSTM input projections and the LinearCRFEncoder (+Clamp) -- reference call sites
 // bonito/nn.py:226,235-241 (Conv1d), :366-370 (LSTM W_ih), :283-298 + :59-67 (Linear, Clamp).
@@ -19,16 +20,17 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, STAGES = 4;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;         // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int EPI_WARPS = 8;
 
 template <int BN>
 struct TcSmem {
     static constexpr uint32_t kA = BM * BK * 2;         // 16 KB
     static constexpr uint32_t kB = BN * BK * 2;         // 16 / 32 KB
     static constexpr uint32_t kStage = kA + kB;
-    static constexpr uint32_t kEpi = STAGES * kStage;        // 4 epilogue warps x (32 rows x 128 B) transpose buffers
-    static constexpr uint32_t kBias = kEpi + 4 * 4096;       // 4 x 512 B: the tile's bias slice, one copy per warp
-    static constexpr uint32_t kBars = kBias + 4 * 512;       // mbarriers after the buffers
+    static constexpr uint32_t kEpi = STAGES * kStage;             // 8 epilogue warps x (32 rows x 64 B) transpose buffers
+    static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;    // 8 x 512 B: the tile's bias slice, one copy per warp
+    static constexpr uint32_t kBars = kBias + EPI_WARPS * 512;    // mbarriers after the buffers
     static constexpr uint32_t kTotal = kBars + 256 + 1024;   // + alignment slack
 };
 
@@ -44,10 +46,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     tc_wait_ld();
 }
 
-// Epilogue of one 128 x BN accumulator tile by one warp (its 32 TMEM lanes = 32 output rows).  A lane owns one row;
-// 64 columns at a time are converted, transposed through a swizzled 32 x 128 B shared-memory buffer and written so
-// that 8 lanes cover 128 contiguous bytes of one output row (full 128-byte lines instead of 32 scattered half-sectors
-// per store instruction).
 // One warp copies the BN bias values of column block `nb` into its shared-memory slice (zeros when there is no bias).
 template <int BN>
 __device__ __forceinline__ void stage_bias(__half* sbias, const __half* __restrict__ bias, int nb, int N, int lane) {
@@ -60,54 +58,86 @@ __device__ __forceinline__ void stage_bias(__half* sbias, const __half* __restri
     __syncwarp();
 }
 
+// Epilogue of one 128 x BN accumulator tile.  Two warps share each 32-lane TMEM quarter (= 32 output rows): warp set
+// `set` takes every other 32-column block, so the two sets drain one accumulator in half the time (the kernels were
+// epilogue-bound with a single set: tile period 5.6k cycles against a 3.4k-cycle mainloop).  A lane owns one row; a block
+// of 32 columns is converted, transposed through a swizzled 32 x 64 B shared-memory buffer and written so that 4 lanes
+// cover 64 contiguous bytes of one output row (two full sectors instead of 32 scattered half-sectors per instruction).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* tbuf, const __half* sbias,
                                               __half* __restrict__ C, long long ldc, int M, int N, int mb, int nb,
-                                              int quarter, int lane, const GemmEpilogue& ep) {
+                                              int quarter, int set, int lane, const GemmEpilogue& ep) {
     const int gm = mb * BM + quarter * 32 + lane;
     const long long orow = (gm < M) ? map_row(ep.map, gm) : -1;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 64) {
-        const int gn0 = nb * BN + c0;
-        if (gn0 >= N) break;  // warp-uniform
+    // 64-B rows: the row's parity picks the half of a 128-B line, (row >> 1) & 3 permutes the four 16-B slots
+    auto stage = [&](int g, const __half2 (&packed)[4]) {
+        *reinterpret_cast<uint4*>(tbuf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(packed);
+    };
+    auto flush = [&](int gcol, int ncols) {   // staged 32 columns -> C[:, gcol .. gcol+31]; ncols = valid output width
+        __syncwarp();
+        const int chunk = lane & 3;
+        const bool col_ok = gcol + chunk * 8 < ncols;   // widths are multiples of 8
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tc_ld32(taddr + c0 + half * 32, v);
+        for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + (lane >> 2);
+            const long long r = __shfl_sync(0xffffffffu, orow, row);
+            const uint4 val = *reinterpret_cast<const uint4*>(tbuf + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+            if (r >= 0 && col_ok) *reinterpret_cast<uint4*>(C + r * ldc + gcol + chunk * 8) = val;
+        }
+        __syncwarp();
+    };
+    if (ep.act == B200_ACT_SWIGLU) {
+        // columns [c0, c0+32) = y, [c0+32, c0+64) = gate of the same 32 features -> 32 outputs per row
+#pragma unroll 1
+        for (int c0 = set * 64; c0 < BN; c0 += 128) {
+            const int gn0 = nb * BN + c0;
+            if (gn0 >= N) break;  // warp-uniform
+            uint32_t vy[32], vg[32];
+            tc_ld_32x32b_x32(taddr + c0, vy);
+            tc_ld_32x32b_x32(taddr + c0 + 32, vg);
+            tc_wait_ld();
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                const int gn = gn0 + half * 32 + g * 8;
                 __half2 packed[4];
-                // bias slice of this tile, staged in shared memory by stage_bias() (a global load here would expose
-                // its full latency 32 times per tile: it was 40 % of the epilogue's stall samples)
-                const uint4 braw = *reinterpret_cast<const uint4*>(sbias + c0 + half * 32 + g * 8);
-                const __half2* bh = reinterpret_cast<const __half2*>(&braw);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float x0 = __uint_as_float(v[g * 8 + 2 * p]) + __low2float(bh[p]);
-                    const float x1 = __uint_as_float(v[g * 8 + 2 * p + 1]) + __high2float(bh[p]);
-                    if (ep.act == B200_ACT_NONE)
-                        packed[p] = __floats2half2_rn(x0, x1);
-                    else
-                        packed[p] = __floats2half2_rn(apply_act_f16(x0, ep.act, ep.lo, ep.hi),
-                                                      apply_act_f16(x1, ep.act, ep.lo, ep.hi));
+                    const float y0 = round_f16(__uint_as_float(vy[g * 8 + 2 * p])), y1 = round_f16(__uint_as_float(vy[g * 8 + 2 * p + 1]));
+                    const float g0 = round_f16(__uint_as_float(vg[g * 8 + 2 * p])), g1 = round_f16(__uint_as_float(vg[g * 8 + 2 * p + 1]));
+                    packed[p] = __floats2half2_rn(g0 * y0 * rcp_approx(1.0f + __expf(-g0)), g1 * y1 * rcp_approx(1.0f + __expf(-g1)));
                 }
-                const int chunk = half * 4 + g;
-                *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = *reinterpret_cast<uint4*>(packed);
+                stage(g, packed);
             }
+            flush(gn0 >> 1, N >> 1);
         }
-        __syncwarp();
-        const int chunk = lane & 7;
-        const bool col_ok = gn0 + chunk * 8 < N;  // N % 8 == 0
+        return;
+    }
+#pragma unroll 1
+    for (int c0 = set * 32; c0 < BN; c0 += 64) {
+        const int gn0 = nb * BN + c0;
+        if (gn0 >= N) break;  // warp-uniform
+        uint32_t v[32];
+        tc_ld32(taddr + c0, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + (lane >> 3);
-            const long long r = __shfl_sync(0xffffffffu, orow, row);
-            const uint4 val = *reinterpret_cast<const uint4*>(tbuf + row * 128 + ((chunk ^ (row & 7)) << 4));
-            if (r >= 0 && col_ok) *reinterpret_cast<uint4*>(C + r * ldc + gn0 + chunk * 8) = val;
+        for (int g = 0; g < 4; ++g) {
+            __half2 packed[4];
+            // bias slice of this tile, staged in shared memory by stage_bias() (a global load here would expose
+            // its full latency 32 times per tile: it was 40 % of the epilogue's stall samples)
+            const uint4 braw = *reinterpret_cast<const uint4*>(sbias + c0 + g * 8);
+            const __half2* bh = reinterpret_cast<const __half2*>(&braw);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float x0 = __uint_as_float(v[g * 8 + 2 * p]) + __low2float(bh[p]);
+                const float x1 = __uint_as_float(v[g * 8 + 2 * p + 1]) + __high2float(bh[p]);
+                if (ep.act == B200_ACT_NONE)
+                    packed[p] = __floats2half2_rn(x0, x1);
+                else
+                    packed[p] = __floats2half2_rn(apply_act_f16(x0, ep.act, ep.lo, ep.hi),
+                                                  apply_act_f16(x1, ep.act, ep.lo, ep.hi));
+            }
+            stage(g, packed);
         }
-        __syncwarp();
+        flush(gn0, N);
     }
 }
 
@@ -140,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(s), EPI_WARPS);  // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -200,9 +230,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ===== epilogue warps (TMEM lanes 32*(warp%4) .. +31) =====
-        const int quarter = warp & 3;
-        unsigned char* tbuf = gen_base + S::kEpi + quarter * 4096;
-        __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + quarter * 512);
+        const int quarter = warp & 3, ew = warp - 2, set = ew >> 2;
+        unsigned char* tbuf = gen_base + S::kEpi + ew * 2048;
+        __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + ew * 512);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -210,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             stage_bias<BN>(sbias, ep.bias, nb, N, lane);   // before the wait: its latency hides behind the mainloop
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, lane, ep);
+            epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, set, lane, ep);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -237,9 +267,9 @@ template <int BN>
 struct WsSmem {
     static constexpr uint32_t kBres = 0;                                  // [WS_KB][BN rows][128 B] SWIZZLE_128B
     static constexpr uint32_t kRing = WS_KB * BN * 128;                   // WS_STAGES x (128 x 64 fp16)
-    static constexpr uint32_t kEpi = kRing + WS_STAGES * BM * BK * 2;     // 4 x 4 KB transpose buffers
-    static constexpr uint32_t kBias = kEpi + 4 * 4096;                    // 4 x 512 B bias slice copies
-    static constexpr uint32_t kBars = kBias + 4 * 512;
+    static constexpr uint32_t kEpi = kRing + WS_STAGES * BM * BK * 2;     // 8 x 2 KB transpose buffers
+    static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;            // 8 x 512 B bias slice copies
+    static constexpr uint32_t kBars = kBias + EPI_WARPS * 512;
     static constexpr uint32_t kTotal = kBars + 256 + 1024;
 };
 
@@ -274,7 +304,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);
+            mbar_init(tempty_bar(s), EPI_WARPS);
         }
         mbar_init(bres_bar, 1);
         mbar_fence_init();
@@ -330,16 +360,16 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ===== epilogue warps =====
-        const int quarter = warp & 3;
-        unsigned char* tbuf = gen_base + S::kEpi + quarter * 4096;
-        __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + quarter * 512);
+        const int quarter = warp & 3, ew = warp - 2, set = ew >> 2;
+        unsigned char* tbuf = gen_base + S::kEpi + ew * 2048;
+        __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + ew * 512);
         stage_bias<BN>(sbias, ep.bias, nb, N, lane);       // the column block never changes
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int mb = mb0; mb < m_blocks; mb += mb_step) {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, lane, ep);
+            epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, set, lane, ep);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));

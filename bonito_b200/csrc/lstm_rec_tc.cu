@@ -13,8 +13,9 @@
 //   * h_{t-1} of a sub-tile [16 chunks x 384] sits in shared memory as the UMMA B operand, K-major WITHOUT swizzle:
 //     [48 k-chunks of 8 units][16 chunks][16 B], so the 8 units x 16 chunks one warp produces are 256 contiguous
 //     bytes of every peer's tile (double buffered by step parity).
-//   * per (step, sub-tile) one elected thread issues 48 tcgen05.mma (M=128, N=16, K=16) -> gate pre-activations in
-//     TMEM; eight epilogue warps pull them with tcgen05.ld.16x256b -- the mma-accumulator fragment, so with rows
+//   * per (step, sub-tile) one elected thread issues 2 x 24 tcgen05.mma (M=128, N=16, K=16) -> gate pre-activations in
+//     TMEM; eight epilogue warps PER SUB-TILE (two independent sets, so the two sub-tiles' cell updates overlap in time
+//     instead of alternating on the same warps: 2412 instead of 2811 cycles per step) pull them with tcgen05.ld.16x256b -- the mma-accumulator fragment, so with rows
 //     ordered [8 units x (i,f,g,o)] one thread holds all four gates of a (unit, chunk) -- add the prefetched input
 //     projection, update (c, h) in registers, stage the new h block in shared memory and push it into the h tile
 //     of all 8 CTAs of the cluster with one bulk copy per peer (cp.async.bulk shared::cta -> shared::cluster; the copy
@@ -37,7 +38,7 @@ constexpr int CS = 8;
 constexpr int UPC = H / CS;        // 48 units per CTA
 constexpr int ROWS = 4 * UPC;      // 192 gate rows per CTA
 constexpr int THREADS = 288;       // 8 epilogue warps + the MMA warp
-constexpr int MMA_WARP = 8;
+constexpr int THREADS_SPLIT = 544; // 2 x 8 epilogue warps (one set per sub-tile) + the MMA warp
 constexpr uint32_t HT = (H / 8) * SN * 16;         // one h tile: 48 k-chunks x 16 chunks x 16 B = 12288 B
 constexpr uint32_t COL_A1 = 0, COL_A2 = 192, COL_D = 384, TMEM_COLS = 512;   // D: [sub][D1|D2] x 16 columns
 constexpr uint32_t STAGE_WARP = SN * 16;           // 256 B per (parity, sub, warp)
@@ -83,7 +84,8 @@ struct RecBars {
 // VARIANT is a timing-experiment knob (B200_LSTM_DEBUG): 0 = product; 1 = all eight copies of the h block go to the
 // CTA's own tile (no inter-SM traffic; wrong results); 2 = cell update replaced by a sum (no SFU work; wrong
 // results); 3 = product + timeline.
-template <int NJ, int VARIANT>
+// SUBSEL: -1 = this warp serves both sub-tiles in turn; 0 / 1 = it serves only that sub-tile (split warp sets).
+template <int NJ, int VARIANT, int SUBSEL>
 __device__ __forceinline__ void epilogue_warp(const __half* __restrict__ gx, __half* __restrict__ y, int T, int N, int reverse,
                                               int n0, uint32_t rank, int blk, int quarter, int which, int col0,
                                               uint32_t tmem_base, uint32_t base, unsigned char* gbase, RecBars bars,
@@ -106,8 +108,10 @@ __device__ __forceinline__ void epilogue_warp(const __half* __restrict__ gx, __h
         for (int j = 0; j < NJ; ++j) c_state[s][j][0] = c_state[s][j][1] = 0.f;
 
     // input pre-activations are prefetched one (step, sub-tile) item ahead: never on the recurrence's critical path
+    constexpr int ITEMS = SUBSEL < 0 ? NS : 1;      // (step, sub-tile) items this warp walks per step
+    const int wslot = warp & 7;                     // staging slot inside the (parity, sub) group
     auto load_gx = [&](int item, uint2 (&dst)[NJ][2]) {
-        const int step = item >> 1, sub = item & 1;
+        const int step = SUBSEL < 0 ? (item >> 1) : item, sub = SUBSEL < 0 ? (item & 1) : SUBSEL;
         const int t = reverse ? (T - 1 - step) : step;
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
@@ -122,18 +126,19 @@ __device__ __forceinline__ void epilogue_warp(const __half* __restrict__ gx, __h
     // of lead let the loads surface on the critical path (3.4 ms instead of 2.5 ms per layer-launch)
     uint2 g[NJ][2], gn[NJ][2], gnn[NJ][2];
     load_gx(0, g);
-    if (T * NS > 1) load_gx(1, gn);
+    if (T * ITEMS > 1) load_gx(1, gn);
 
     for (int step = 0; step < T; ++step) {
         const int t = reverse ? (T - 1 - step) : step;
         const int p = step & 1;
 #pragma unroll
         for (int sub = 0; sub < NS; ++sub) {
-            const int item = step * NS + sub;
+            if (SUBSEL >= 0 && sub != SUBSEL) continue;
+            const int item = SUBSEL < 0 ? step * NS + sub : step;
             // staging buffer (parity, sub): its last readers (bulk copies of step-2) are complete, see kernel comment
-            const uint32_t stage_off = OFF_STAGE + (uint32_t)((p * NS + sub) * 8 + warp) * STAGE_WARP;
+            const uint32_t stage_off = OFF_STAGE + (uint32_t)((p * NS + sub) * 8 + wslot) * STAGE_WARP;
             __half* stage = reinterpret_cast<__half*>(gbase + stage_off);
-            if (item + 2 < T * NS) load_gx(item + 2, gnn);
+            if (item + 2 < T * ITEMS) load_gx(item + 2, gnn);
             mbar_wait(bars.dfull + 8 * sub, (uint32_t)(step & 1));
             const bool tl = VARIANT == 3 && sub == 0 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7);
             const int ts = step % TL_STEPS;
@@ -209,8 +214,11 @@ __device__ __forceinline__ void epilogue_warp(const __half* __restrict__ gx, __h
 //   warps 0-3 (16 chunks/sub-tile)  block 0 (acc 0)    block 1 (acc 0)    block 4 (acc 1)     block 5 (acc 1)
 //   warps 4-7 ( 8 chunks/sub-tile)  block 2 (acc 1) 0-7  block 3 (acc 1) 0-7  block 2 (acc 0) 8-15  block 3 (acc 0) 8-15
 //   warp 8                          MMA issuer (+ TMEM allocation)
-template <int VARIANT>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(THREADS, 1)
+//
+// SPLIT = 1: two sets of eight epilogue warps, one per sub-tile (17 warps), so the two sub-tiles' epilogues overlap in
+// time instead of alternating on the same warps.
+template <int VARIANT, int SPLIT>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(SPLIT ? THREADS_SPLIT : THREADS, 1)
 lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh, __half* __restrict__ y, int T, int N,
                    int reverse) {
     extern __shared__ unsigned char smem_raw[];
@@ -222,6 +230,7 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
     const uint32_t tmem_slot = bars.dfull + 8 * 2;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int MMA_WARP = SPLIT ? 16 : 8;
     const uint32_t rank = cluster_ctarank();
     const int group = blockIdx.x / CS;
     const int n0 = group * NB;
@@ -238,7 +247,7 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
     }
     if (warp == MMA_WARP) tc_alloc(tmem_slot, TMEM_COLS);
     // h_{-1} = 0 (parity 0 tiles of both sub-tiles; zeroing everything is simplest)
-    for (int i = tid; i < (int)(NS * 2 * HT / 16); i += THREADS) reinterpret_cast<uint4*>(gbase + OFF_H)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(NS * 2 * HT / 16); i += (int)blockDim.x) reinterpret_cast<uint4*>(gbase + OFF_H)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -309,16 +318,22 @@ lstm_rec_tc_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh
             }
         }
     } else {
-        const int quarter = warp & 3;
-        if (warp < 4) {
-            const int blk = quarter < 2 ? quarter : quarter + 2;              // 0, 1, 4, 5
-            epilogue_warp<2, VARIANT>(gx, y, T, N, reverse, n0, rank, blk, quarter, quarter < 2 ? 0 : 1, 0, tmem_base, base,
-                                      gbase, bars, warp, lane);
+        const int quarter = warp & 3, ew = warp & 7;
+        const int blk = ew < 4 ? (quarter < 2 ? quarter : quarter + 2)        // 0, 1, 4, 5
+                               : 2 + (quarter & 1);                           // 2, 3, 2, 3
+        const int which = ew < 4 ? (quarter < 2 ? 0 : 1) : (quarter < 2 ? 1 : 0);
+        const int col0 = ew < 4 ? 0 : (quarter < 2 ? 0 : 8);
+#define RUN_EPILOGUE(NJ_, SEL_)                                                                                          \
+        epilogue_warp<NJ_, VARIANT, SEL_>(gx, y, T, N, reverse, n0, rank, blk, quarter, which, col0, tmem_base, base, gbase, \
+                                          bars, warp, lane)
+        if (!SPLIT) {
+            if (ew < 4) RUN_EPILOGUE(2, -1); else RUN_EPILOGUE(1, -1);
+        } else if (warp < 8) {
+            if (ew < 4) RUN_EPILOGUE(2, 0); else RUN_EPILOGUE(1, 0);
         } else {
-            const int blk = 2 + (quarter & 1);                                // 2, 3, 2, 3
-            epilogue_warp<1, VARIANT>(gx, y, T, N, reverse, n0, rank, blk, quarter, quarter < 2 ? 1 : 0, quarter < 2 ? 0 : 8,
-                                      tmem_base, base, gbase, bars, warp, lane);
+            if (ew < 4) RUN_EPILOGUE(2, 1); else RUN_EPILOGUE(1, 1);
         }
+#undef RUN_EPILOGUE
     }
 
     tc_fence_before();
@@ -420,16 +435,21 @@ int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, in
     const int groups = (N + NB - 1) / NB;
     const char* dbg = getenv("B200_LSTM_DEBUG");
     const int variant = dbg ? atoi(dbg) : 0;
-#define LAUNCH_VARIANT(v)                                                                                          \
-    do {                                                                                                           \
-        B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<v>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                             (int)SMEM_BYTES));                                                    \
-        lstm_rec_tc_kernel<v><<<groups * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, T, N, reverse);            \
+    const char* sp = getenv("B200_LSTM_SPLIT");
+    const bool split = sp ? atoi(sp) != 0 : true;   // measured: 2412 vs 2811 cycles per step (profiles/r01_lstm_split.md)
+#define LAUNCH_VARIANT(v, s)                                                                                          \
+    do {                                                                                                              \
+        B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<v, s>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                             (int)SMEM_BYTES));                                                       \
+        lstm_rec_tc_kernel<v, s><<<groups * CS, s ? THREADS_SPLIT : THREADS, SMEM_BYTES, stream>>>(gx, whh, y, T, N,  \
+                                                                                                   reverse);         \
     } while (0)
-    if (variant == 3) LAUNCH_VARIANT(3);
-    else if (variant == 1) LAUNCH_VARIANT(1);
-    else if (variant == 2) LAUNCH_VARIANT(2);
-    else LAUNCH_VARIANT(0);
+    if (variant == 3 && split) LAUNCH_VARIANT(3, 1);
+    else if (variant == 3) LAUNCH_VARIANT(3, 0);
+    else if (variant == 1) LAUNCH_VARIANT(1, 0);
+    else if (variant == 2) LAUNCH_VARIANT(2, 0);
+    else if (split) LAUNCH_VARIANT(0, 1);
+    else LAUNCH_VARIANT(0, 0);
 #undef LAUNCH_VARIANT
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -448,10 +468,10 @@ int lstm_rec_tc_max_clusters() {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaFuncSetAttribute(lstm_rec_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(lstm_rec_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
         return -1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, lstm_rec_tc_kernel<0>, &cfg) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_rec_tc_kernel<0, 0>, &cfg) != cudaSuccess) return -1;
     return n;
 }
 

@@ -13,11 +13,24 @@ QKV GEMM -> rotary + windowed attention -> out-proj GEMM (+bias) -> residual RMS
 residual RMSNorm, then the upsample GEMM (+bias; the x2 reshape is free in a batch-first layout) and the CRF GEMM (x scale).
 """
 
+import os
+
 import torch
 
 from bonito_b200 import native
 from bonito_b200 import nn as bnn
 from bonito_b200.engine import UnsupportedModel, _Stage, _act_code, _dev16, _folded_conv
+
+# SwiGLU formed in the fc1 GEMM's epilogue (B200_ACT_SWIGLU); B200_FUSE_SWIGLU=0 keeps the separate kernel as a cross-check
+FUSE_SWIGLU = os.environ.get("B200_FUSE_SWIGLU", "1") != "0"
+
+
+def _interleave_swiglu(w1):
+    """fc1.weight [2F, d] (rows: y then gate, GatedMlp's chunk(2)) -> rows in 64-groups [32 y | 32 gate] of the same features."""
+    f = w1.shape[0] // 2
+    assert f % 32 == 0, "fused SwiGLU needs dim_feedforward % 32 == 0"
+    y, g = w1[:f].reshape(f // 32, 32, -1), w1[f:].reshape(f // 32, 32, -1)
+    return torch.cat([y, g], dim=1).reshape(2 * f, -1).contiguous()
 
 
 def find_transformer_encoder(encoder):
@@ -64,7 +77,9 @@ class TransformerPlan:
                 wqkv=_dev16(a.Wqkv.weight.detach(), dev),
                 wo=_dev16(a.out_proj.weight.detach(), dev),
                 bo=_dev16(None if a.out_proj.bias is None else a.out_proj.bias.detach(), dev),
-                w1=_dev16(layer.ff.fc1.weight.detach(), dev), w2=_dev16(layer.ff.fc2.weight.detach(), dev),
+                w1=_dev16(_interleave_swiglu(layer.ff.fc1.weight.detach()), dev) if FUSE_SWIGLU else
+                _dev16(layer.ff.fc1.weight.detach(), dev),
+                w2=_dev16(layer.ff.fc2.weight.detach(), dev),
                 n1=_dev16(layer.norm1.weight.detach(), dev), n2=_dev16(layer.norm2.weight.detach(), dev),
                 eps=float(layer.norm1.eps),
                 # deepnorm_alpha is a buffer that model.half() rounds to fp16 (2.4494897 -> 2.4492188)
@@ -119,7 +134,7 @@ class TransformerPlan:
             bufs.update(T=Tq, M=M,
                         xa=torch.empty(M, d, dtype=f16, device=dev), xb=torch.empty(M, d, dtype=f16, device=dev),
                         qkv=torch.empty(M, 3 * d, dtype=f16, device=dev), att=torch.empty(M, d, dtype=f16, device=dev),
-                        proj=torch.empty(M, d, dtype=f16, device=dev), h1=torch.empty(M, 2 * ff, dtype=f16, device=dev),
+                        proj=torch.empty(M, d, dtype=f16, device=dev), h1=None if FUSE_SWIGLU else torch.empty(M, 2 * ff, dtype=f16, device=dev),
                         g=torch.empty(M, ff, dtype=f16, device=dev),
                         up=torch.empty(M, self.up_factor * d, dtype=f16, device=dev))
             inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.float32, device=dev) / 64))
@@ -169,10 +184,14 @@ class TransformerPlan:
             with stage("rmsnorm"):
                 native.rmsnorm_residual(b["proj"], cur, l["n1"], l["alpha"], l["eps"], nxt, M, d)
             cur, nxt = nxt, cur
-            with stage("fc1_gemm"):
-                native.gemm(cur, d, l["w1"], None, b["h1"], 2 * ff, M, 2 * ff, d)
-            with stage("swiglu"):
-                native.swiglu(b["h1"], b["g"], M, ff)
+            if FUSE_SWIGLU:
+                with stage("fc1_swiglu_gemm"):   # y * silu(gate) formed in the GEMM epilogue: h1 never reaches HBM
+                    native.gemm(cur, d, l["w1"], None, b["g"], ff, M, 2 * ff, d, act=native.ACT_SWIGLU)
+            else:
+                with stage("fc1_gemm"):
+                    native.gemm(cur, d, l["w1"], None, b["h1"], 2 * ff, M, 2 * ff, d)
+                with stage("swiglu"):
+                    native.swiglu(b["h1"], b["g"], M, ff)
             with stage("fc2_gemm"):
                 native.gemm(b["g"], ff, l["w2"], None, b["proj"], d, M, d, ff)
             with stage("rmsnorm"):

@@ -33,6 +33,11 @@ extern "C" {
 #define B200_ACT_TANH 2
 #define B200_ACT_CLAMP 3 /* clamp(lo, hi), Clamp layer: bonito/nn.py:59-67 */
 #define B200_ACT_SCALE 4 /* multiply by lo, LinearCRFEncoder.scale: bonito/nn.py:288-289 */
+/* SwiGLU fused into the GEMM (tcgen05 path only): the n output columns are 64-wide groups [32 x y | 32 x gate] (the caller
+ * interleaves the rows of fc1.weight that way) and c receives n/2 columns, c[:, 32*g + j] = gate * y / (1 + exp(-gate)) on the
+ * fp16-rounded y / gate, rounded once -- GatedMlp: flash_attn/modules/mlp.py:99-136, flash_attn/ops/activations.py:107-111
+ * as used by bonito/transformer/model.py:100-104.  n % 64 == 0, no bias. */
+#define B200_ACT_SWIGLU 5
 
 #define B200_GEMM_AUTO 0 /* tcgen05 (product path) unless B200_GEMM_IMPL=mma is set in the environment */
 #define B200_GEMM_TCGEN05 1

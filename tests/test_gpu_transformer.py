@@ -116,3 +116,24 @@ def test_sup_model_call_and_decode():
     got = [r[r != 0].tobytes() for r in seq.numpy()]
     want = [r[r != 0].tobytes() for r in o_seq]
     assert got == want and min(len(w) for w in want) > 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,k,f", [(1000, 512, 2048), (77, 384, 96), (4096, 512, 256), (2000, 384, 192)])
+def test_gemm_with_fused_swiglu(native, m, k, f):
+    """B200_ACT_SWIGLU: fc1 with rows interleaved in [32 y | 32 gate] groups == GatedMlp's fc1 -> chunk -> swiglu."""
+    from bonito_b200.engine_tf import _interleave_swiglu
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(m, k, generator=g).half()
+    w1 = (torch.randn(2 * f, k, generator=g) / k ** 0.5 * 2).half()
+    out = torch.full((m, f), float("nan"), dtype=torch.float16, device="cuda")
+    native.gemm(_dev(x), k, _dev(_interleave_swiglu(w1)), None, out, f, m, 2 * f, k, act=native.ACT_SWIGLU)
+    h = (x.float() @ w1.float().t()).half().float()
+    y, gate = h.chunk(2, dim=-1)
+    ref = (gate * y / (1 + torch.exp(-gate))).half().float()
+    err = (out.float().cpu() - ref).abs()
+    # y / gate are rounded to fp16 before the product, so a 1-ulp difference in either (accumulation order) moves the
+    # result by up to 2^-10 relative each, plus the final rounding
+    assert bool(torch.all(err <= 4e-3 + 4e-3 * ref.abs())) and err.mean().item() <= 2e-4, (err.max().item(), err.mean().item())
+    with pytest.raises(RuntimeError):
+        native.gemm(_dev(x), k, _dev(w1), None, out, f, m, 2 * f, k, act=native.ACT_SWIGLU, impl=native.GEMM_MMA_SYNC)
