@@ -17,6 +17,8 @@
 //   pass 3: trace-back through the back-pointers (staged through shared memory in blocks)
 // Tie-breaks (the reference's are whatever argmax over koi's Max-semiring gradient gives):
 // lowest in-edge index, lowest final state.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -267,7 +269,12 @@ int launch_decode(const __half* scores, int N, int T, float blank, float qscale,
     double* bsum = reinterpret_cast<double*>(ws + off); off += align256((size_t)N * (T + 1) * sizeof(double));
     float* pm = reinterpret_cast<float*>(ws + off); off += align256((size_t)N * T * 4 * sizeof(float));
     uint8_t* bp = ws + off;
-    const size_t dyn = DecodeSmem<S>::bytes(T);
+    size_t dyn = DecodeSmem<S>::bytes(T);
+    // B200_DECODE_SMEM_KB pads the request to bound the CTAs per SM (room for a co-resident recurrent CTA)
+    if (const char* pad = getenv("B200_DECODE_SMEM_KB")) {
+        const size_t want = (size_t)atoi(pad) * 1024;
+        if (want > dyn && want <= 200 * 1024) dyn = want;
+    }
     auto kern = crf_decode_kernel<S>;
     B200_REQUIRE(dyn <= 200 * 1024, "crf_decode: chunk of %d frames needs %zu B of shared memory", T, dyn);
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));

@@ -435,13 +435,17 @@ int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, in
     const int groups = (N + NB - 1) / NB;
     const char* dbg = getenv("B200_LSTM_DEBUG");
     const int variant = dbg ? atoi(dbg) : 0;
+    // experiments: B200_LSTM_SMEM_KB shrinks the shared-memory request (the split kernel cannot be co-resident with itself
+    // anyway: 544 threads x 85 registers), which lets small CTAs of other kernels share the SM
+    const char* skb = getenv("B200_LSTM_SMEM_KB");
+    const uint32_t smem_bytes = skb && (uint32_t)atoi(skb) * 1024u >= SMEM_USED ? (uint32_t)atoi(skb) * 1024u : SMEM_BYTES;
     const char* sp = getenv("B200_LSTM_SPLIT");
     const bool split = sp ? atoi(sp) != 0 : true;   // measured: 2412 vs 2811 cycles per step (profiles/r01_lstm_split.md)
 #define LAUNCH_VARIANT(v, s)                                                                                          \
     do {                                                                                                              \
         B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<v, s>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                             (int)SMEM_BYTES));                                                       \
-        lstm_rec_tc_kernel<v, s><<<groups * CS, s ? THREADS_SPLIT : THREADS, SMEM_BYTES, stream>>>(gx, whh, y, T, N,  \
+                                             (int)smem_bytes));                                                       \
+        lstm_rec_tc_kernel<v, s><<<groups * CS, s ? THREADS_SPLIT : THREADS, smem_bytes, stream>>>(gx, whh, y, T, N,  \
                                                                                                    reverse);         \
     } while (0)
     if (variant == 3 && split) LAUNCH_VARIANT(3, 1);
