@@ -58,6 +58,82 @@ def compute_scores(model, batch, beam_width=32, beam_cut=100.0, scale=1.0, offse
         return {"moves": moves, "qstring": qstring, "sequence": sequence}
 
 
+class _Slot:
+    """Staging of one in-flight batch: pinned fp16 input, device input, device + pinned result arrays, two events."""
+
+    def __init__(self, shape, device):
+        self.pinned_in = torch.empty(shape, dtype=torch.float16, pin_memory=True)
+        self.dev_in = torch.empty(shape, dtype=torch.float16, device=device)
+        self.dev_out = self.pinned_out = None          # uint8 [3, N, T] (moves, sequence, qstring), sized on first use
+        self.in_ready, self.done = torch.cuda.Event(), torch.cuda.Event()
+        self.key = None
+
+
+def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=1.0, offset=0.0, blank_score=2.0,
+                  reverse=False):
+    """
+    `compute_scores` over an iterable of (key, float32 host batch), yielding (key, result) in order, as a `depth`-deep
+    pipeline: the fp16 cast + H2D copy of batch k+1 (copy stream) and the D2H copy of batch k-1 overlap the kernels of
+    batch k, and the host does not wait for the GPU before the next batch is enqueued.  This is the loop `basecall()` runs
+    (the reference overlaps the same stages with a background thread, bonito/crf/basecall.py:70-72); results are
+    identical to calling `compute_scores` batch by batch.
+    """
+    from bonito_b200.decode import _decoder
+    device = next(model.parameters()).device
+    if device.type != "cuda":
+        raise RuntimeError("bonito_b200 needs a CUDA device (there is no CPU path)")
+    rings, pending = {}, []          # input shape -> [slots, next]; FIFO of slots whose results are not handed out yet
+    copy_stream = torch.cuda.Stream(device=device)
+
+    def result_of(slot):
+        slot.done.synchronize()
+        moves, sequence, qstring = slot.pinned_out.clone().unbind(0)    # the pinned buffer is reused `depth` batches later
+        return slot.key, {"moves": moves, "qstring": qstring, "sequence": sequence}
+
+    def enqueue(slot, key, batch):
+        with torch.inference_mode(), torch.cuda.device(device):
+            main = torch.cuda.current_stream()
+            slot.key = key
+            slot.pinned_in.copy_(batch)              # fp32 -> fp16 on the host, as the reference does
+            with torch.cuda.stream(copy_stream):
+                slot.dev_in.copy_(slot.pinned_in, non_blocking=True)
+                slot.in_ready.record(copy_stream)
+            main.wait_event(slot.in_ready)
+            scores = model(slot.dev_in)
+            if reverse:
+                scores = _revcomp_native(model, scores, blank_score)
+            n, t, c = scores.shape
+            if slot.dev_out is None:
+                slot.dev_out = torch.empty(3, n, t, dtype=torch.uint8, device=device)
+                slot.pinned_out = torch.empty(3, n, t, dtype=torch.uint8, pin_memory=True)
+            state_len = int(round(np.log(c) / np.log(4))) - 1
+            _decoder(scores, state_len, blank_score=blank_score, qscale=scale, qbias=offset, out=slot.dev_out)
+            slot.pinned_out.copy_(slot.dev_out, non_blocking=True)
+            slot.done.record(main)
+
+    for key, batch in batches:
+        shape = tuple(batch.shape)
+        if shape not in rings:
+            if len(rings) > 4:                       # many geometries seen: hand out what is in flight, drop old staging
+                while pending:
+                    yield result_of(pending.pop(0))
+                rings.clear()
+            rings[shape] = [[_Slot(shape, device) for _ in range(depth)], 0]
+            # the new device buffers may reuse memory that kernels already enqueued on the compute stream still touch (the
+            # caching allocator only orders reuse on the allocating stream): the copy stream must not write them earlier
+            with torch.cuda.device(device):
+                copy_stream.wait_stream(torch.cuda.current_stream())
+        ring = rings[shape]
+        slot = ring[0][ring[1]]
+        ring[1] = (ring[1] + 1) % depth
+        while any(p is slot for p in pending):       # the slot's previous batch is handed out before the slot is reused
+            yield result_of(pending.pop(0))
+        enqueue(slot, key, batch)
+        pending.append(slot)
+    while pending:
+        yield result_of(pending.pop(0))
+
+
 def _revcomp_native(model, scores, blank_score):
     """[N,T,C] (no blanks) -> reverse-complemented [N,T,C] through the reference's [T,N,C+blanks] definition."""
     n, t, c = scores.shape
@@ -87,9 +163,7 @@ def basecall(model, reads, chunksize=4000, overlap=100, batchsize=32, reverse=Fa
         for read in reads
     )
     batches = thread_iter(batchify(chunks, batchsize=batchsize))
-    scores = thread_iter(
-        (key, compute_scores(model, batch, reverse=reverse, scale=qscale, offset=qbias)) for key, batch in batches
-    )
+    scores = thread_iter(score_batches(model, batches, reverse=reverse, scale=qscale, offset=qbias))
     results = thread_iter(
         (read, stitch_results(out, end - start, chunksize, overlap, model.stride, reverse))
         for ((read, start, end), out) in unbatchify(scores)

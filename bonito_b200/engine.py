@@ -428,18 +428,23 @@ class CrfDecoder:
     def __init__(self):
         self._ws = None
 
-    def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0, events=None):
+    def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0, events=None, out=None):
+        """-> (moves, sequence, qstring) uint8 [N, T] on the device; `out`: optional uint8 [3, N, T] to write them into."""
         n, t, c = scores.shape
         if c != 4 ** (state_len + 1):
             raise ValueError(f"scores width {c} does not match state_len {state_len}")
         cached = DECODE_CACHE.take(scores, (state_len, float(blank_score), float(qscale), float(qbias)))
         if cached is not None:
+            if out is not None:
+                for dst, src in zip(out, cached):
+                    dst.copy_(src)
+                return tuple(out)
             return cached
         scores = scores.to(torch.float16).contiguous()
         need = native.crf_decode_workspace_bytes(n, t, state_len)
         if self._ws is None or self._ws.numel() < need or self._ws.device != scores.device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=scores.device)
-        outs = [torch.empty(n, t, dtype=torch.uint8, device=scores.device) for _ in range(3)]
+        outs = list(out) if out is not None else [torch.empty(n, t, dtype=torch.uint8, device=scores.device) for _ in range(3)]
         with _Stage("crf_decode", events):
             native.crf_decode(scores, state_len, blank_score, qscale, qbias, self._ws, *outs)
         return tuple(outs)  # moves, sequence, qstring

@@ -183,3 +183,21 @@ def test_cli_basecaller_end_to_end(tmp_path):
     p = model.config["basecaller"]
     for read, res in basecall(model, reads, batchsize=p["batchsize"], chunksize=p["chunksize"], overlap=p["overlap"]):
         assert records[read.read_id] == (res["sequence"], res["qstring"]) and len(res["sequence"]) > 50
+
+
+def test_score_batches_equals_compute_scores():
+    """The pipelined generator basecall() runs == one synchronous compute_scores per batch: same bytes, same order, ragged
+    last batch, chunk length that is not a multiple of the stride, empty input."""
+    from bonito_b200.crf.basecall import compute_scores, score_batches
+    model, spec, weights = _model("fast", n_lstm=3, seed=4)
+    sizes = [(5, 1998), (5, 1998), (5, 1998), (3, 1998), (2, 4000), (5, 1998)]
+    batches = [(f"k{i}", synth.squiggle(n, L, seed=20 + i)) for i, (n, L) in enumerate(sizes)]
+    got = list(score_batches(model, iter(batches), scale=1.05, offset=0.2))
+    assert [k for k, _ in got] == [k for k, _ in batches]
+    for (key, batch), (_, res) in zip(batches, got):
+        want = compute_scores(model, batch, scale=1.05, offset=0.2)
+        for name in ("moves", "sequence", "qstring"):
+            assert res[name].shape == want[name].shape and res[name].dtype == torch.uint8
+            assert torch.equal(res[name], want[name]), (key, name)
+        assert int(res["moves"].sum()) > 10
+    assert list(score_batches(model, iter([]))) == []
