@@ -258,6 +258,246 @@ crf_decode_kernel(const __half* __restrict__ scores, int T, float blank, float q
     }
 }
 
+// ---- v2: the same arithmetic, step loops unrolled by two ---------------------------------------------------------------
+// Every buffer that flips with the step parity (buf, vit, msh, part) is indexed by a compile-time constant inside a step
+// body instantiated for parity 0 and 1, and the global-memory cursors are running pointers: about a third of the v1 loop
+// was address arithmetic.  Results are bit-identical to v1 (same operations in the same order).
+template <int V>
+struct IntC { static constexpr int value = V; };
+
+template <int S>
+__global__ void __launch_bounds__(S)
+crf_decode_kernel_v2(const __half* __restrict__ scores, int T, float blank, float qscale, float qbias,
+                     float* __restrict__ ws_beta, double* __restrict__ ws_bsum, uint8_t* __restrict__ ws_bp,
+                     float* __restrict__ ws_pm, uint8_t* __restrict__ moves, uint8_t* __restrict__ seq,
+                     uint8_t* __restrict__ qual) {
+    using L = DecodeSmem<S>;
+    constexpr int Q = S / 4, NW = L::NW, TB = L::TB;
+    extern __shared__ __align__(16) unsigned char sm[];
+    float (*buf)[S] = reinterpret_cast<float (*)[S]>(sm + L::kBuf);
+    float (*vit)[S] = reinterpret_cast<float (*)[S]>(sm + L::kVit);
+    float (*msh)[4 * S] = reinterpret_cast<float (*)[4 * S]>(sm + L::kUnion);
+    uint8_t (*bp_blk)[S] = reinterpret_cast<uint8_t (*)[S]>(sm + L::kUnion);
+    float (*part)[NW][4] = reinterpret_cast<float (*)[NW][4]>(sm + L::kPart);
+    float* red = reinterpret_cast<float*>(sm + L::kRed);
+    int* red_i = reinterpret_cast<int*>(sm + L::kRedI);
+    uint8_t* out_sh = sm + L::kOut;
+    __shared__ float logz_sh;
+
+    const int n = blockIdx.x;
+    const int s = threadIdx.x;
+    const int lane = s & 31, warp = s >> 5;
+    const uint2* sc = reinterpret_cast<const uint2*>(scores + (size_t)n * T * S * 4) + s;  // row stride S
+    float* beta = ws_beta + (size_t)n * (T + 1) * S;
+    double* bsum = ws_bsum + (size_t)n * (T + 1);
+    uint8_t* bp = ws_bp + (size_t)n * T * S;
+    float* pm = ws_pm + (size_t)n * T * 4;
+
+    // ---------------- pass 1: backward ----------------
+    {
+        buf[0][s] = 0.f;
+        beta[(size_t)T * S + s] = 0.f;
+        if (s == 0) bsum[T] = 0.0;
+        {
+            const uint2 raw = sc[(size_t)(T - 1) * S];
+            const __half2 m01 = *reinterpret_cast<const __half2*>(&raw.x);
+            const __half2 m23 = *reinterpret_cast<const __half2*>(&raw.y);
+            msh[0][0 * S + s] = __low2float(m01); msh[0][1 * S + s] = __high2float(m01);
+            msh[0][2 * S + s] = __low2float(m23); msh[0][3 * S + s] = __high2float(m23);
+        }
+        uint2 raw_next = (T > 1) ? sc[(size_t)(T - 2) * S] : make_uint2(0, 0);
+        const uint2* sc_pf = sc + (size_t)(T - 3) * S;        // next prefetch: row t-2 of the step being processed
+        float* beta_p = beta + (size_t)(T - 1) * S + s;
+        double* bsum_p = bsum + (T - 1);
+        double acc_shift = 0.0;
+        __syncthreads();
+        auto bwd = [&](int t, auto cur_c) {
+            constexpr int CUR = decltype(cur_c)::value;
+            if (t > 0) {
+                const __half2 m01 = *reinterpret_cast<const __half2*>(&raw_next.x);
+                const __half2 m23 = *reinterpret_cast<const __half2*>(&raw_next.y);
+                msh[CUR ^ 1][0 * S + s] = __low2float(m01); msh[CUR ^ 1][1 * S + s] = __high2float(m01);
+                msh[CUR ^ 1][2 * S + s] = __low2float(m23); msh[CUR ^ 1][3 * S + s] = __high2float(m23);
+            }
+            if (t > 1) raw_next = *sc_pf;
+            sc_pf -= S;
+            const float b0 = buf[CUR][0];
+            const float4 mv = *reinterpret_cast<const float4*>(&msh[CUR][4 * s]);
+            const float4 bs = *reinterpret_cast<const float4*>(&buf[CUR][4 * (s % Q)]);
+            const float stay = blank + buf[CUR][s] - b0;
+            const float v = lse5(stay, mv.x + bs.x - b0, mv.y + bs.y - b0, mv.z + bs.z - b0, mv.w + bs.w - b0);
+            acc_shift += (double)b0;
+            buf[CUR ^ 1][s] = v;
+            *beta_p = v;
+            beta_p -= S;
+            if (s == 0) *bsum_p = acc_shift;
+            --bsum_p;
+            __syncthreads();
+        };
+        int t = T - 1;
+        for (; t >= 1; t -= 2) { bwd(t, IntC<0>()); bwd(t - 1, IntC<1>()); }
+        if (t == 0) bwd(0, IntC<0>());
+        // logZ = bsum[0] + LSE_s beta'_0[s]
+        const float v = buf[T & 1][s];
+        float mx = v;
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        mx = red[0];
+        for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red[w]);
+        __syncthreads();
+        float ex = __expf(v - mx);
+        for (int o = 16; o > 0; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
+        if (lane == 0) red[warp] = ex;
+        __syncthreads();
+        if (s == 0) {
+            float tot = 0.f;
+            for (int w = 0; w < NW; ++w) tot += red[w];
+            logz_sh = mx + __logf(tot);
+        }
+        __syncthreads();
+    }
+
+    // ---------------- pass 2: forward + posteriors + Viterbi ----------------
+    {
+        const double logz = bsum[0] + (double)logz_sh;
+        const int pq = s / 4;  // predecessor along in-edge 1+j is j*Q + pq
+        buf[0][s] = 0.f;
+        vit[0][s] = 0.f;
+        double asum = 0.0;
+        __syncthreads();
+        uint2 mraw = sc[0];
+        float bnext = beta[(size_t)1 * S + s], bnext0 = beta[(size_t)1 * S];
+        double bs_next = bsum[1];
+        const uint2* sc_p = sc + S;                       // row t+1
+        const float* beta_p = beta + (size_t)2 * S;       // row t+2
+        const double* bsum_p = bsum + 2;
+        uint8_t* bp_p = bp + s;
+        float* pm_p = pm + s;                             // used by threads 0..3
+        auto fwd = [&](int t, auto cur_c) {
+            constexpr int CUR = decltype(cur_c)::value;
+            uint2 mraw_n = make_uint2(0, 0);
+            float bn_n = 0.f, bn0_n = 0.f;
+            double bsn_n = 0.0;
+            if (t + 1 < T) {  // prefetch: none of this depends on the recurrence
+                mraw_n = *sc_p;
+                bn_n = beta_p[s];
+                bn0_n = beta_p[0];
+                bsn_n = *bsum_p;
+            }
+            sc_p += S; beta_p += S; ++bsum_p;
+            const __half2 m01 = *reinterpret_cast<const __half2*>(&mraw.x);
+            const __half2 m23 = *reinterpret_cast<const __half2*>(&mraw.y);
+            const float ms[5] = {blank, __low2float(m01), __high2float(m01), __low2float(m23), __high2float(m23)};
+            const float a0 = buf[CUR][0];
+            const float v0 = vit[CUR][0];
+            float ap[5], vp[5];
+            ap[0] = buf[CUR][s] - a0;
+            vp[0] = vit[CUR][s] - v0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ap[1 + j] = buf[CUR][j * Q + pq] - a0;
+                vp[1 + j] = vit[CUR][j * Q + pq] - v0;
+            }
+            // per-step normaliser (identical in every thread)
+            const float kt = (float)((double)a0 + asum + (double)bnext0 + bs_next - logz);
+            const float bshift = bnext - bnext0 + kt;
+            float x[5], best = -INFINITY, mass = 0.f;
+            int arg = 0;
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+                x[e] = ap[e] + ms[e];
+                const float post = __expf(x[e] + bshift);
+                if (e > 0) mass += post;
+                const float cand = __logf(post + 1e-8f) + vp[e];
+                if (cand > best) { best = cand; arg = e; }
+            }
+            const float anew = lse5(x[0], x[1], x[2], x[3], x[4]);
+            asum += (double)a0;
+            buf[CUR ^ 1][s] = anew;
+            vit[CUR ^ 1][s] = best;
+            *bp_p = (uint8_t)arg;
+            bp_p += S;
+            // move mass per emitted base (s % 4): reduce lanes of equal lane%4
+            mass += __shfl_xor_sync(0xffffffffu, mass, 4);
+            mass += __shfl_xor_sync(0xffffffffu, mass, 8);
+            mass += __shfl_xor_sync(0xffffffffu, mass, 16);
+            if (lane < 4) part[CUR][warp][lane] = mass;
+            mraw = mraw_n; bnext = bn_n; bnext0 = bn0_n; bs_next = bsn_n;
+            __syncthreads();
+            if (s < 4) {
+                float tot = 0.f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) tot += part[CUR][w][s];
+                *pm_p = tot;
+            }
+            pm_p += 4;
+        };
+        int t = 0;
+        for (; t + 1 < T; t += 2) { fwd(t, IntC<0>()); fwd(t + 1, IntC<1>()); }
+        if (t < T) fwd(t, IntC<0>());
+        // best final state: max Viterbi score, lowest state on ties
+        float v = vit[T & 1][s];
+        int idx = s;
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if (lane == 0) { red[warp] = v; red_i[warp] = idx; }
+        __syncthreads();
+    }
+
+    // ---------------- pass 3: trace-back (as v1) ----------------
+    {
+        uint8_t* o_mov = out_sh;
+        uint8_t* o_seq = out_sh + T;
+        uint8_t* o_q = out_sh + 2 * T;
+        int state = 0;
+        if (s == 0) {
+            float v = red[0];
+            state = red_i[0];
+            for (int w = 1; w < NW; ++w)
+                if (red[w] > v) { v = red[w]; state = red_i[w]; }
+        }
+        for (int hi = T; hi > 0; hi -= TB) {
+            const int lo = max(hi - TB, 0), rows = hi - lo;
+            __syncthreads();
+            for (int i = s; i < rows * (S / 16); i += S) {
+                const int row = i / (S / 16), c = i % (S / 16);
+                *reinterpret_cast<uint4*>(&bp_blk[row][c * 16]) =
+                    *reinterpret_cast<const uint4*>(bp + (size_t)(lo + row) * S + c * 16);
+            }
+            __syncthreads();
+            if (s == 0) {
+                for (int t = hi - 1; t >= lo; --t) {
+                    const int e = bp_blk[t - lo][state];
+                    const int base = state & 3;
+                    if (e != 0) {
+                        const float p = pm[(size_t)t * 4 + base];
+                        const float err = fmaxf(1.0f - p, 1e-4f);
+                        const float qv = -10.0f * log10f(err) * qscale + qbias;
+                        int qi = (int)rintf(qv) + 33;
+                        qi = min(max(qi, 33), 126);
+                        o_mov[t] = 1;
+                        o_seq[t] = (uint8_t)("ACGT"[base]);
+                        o_q[t] = (uint8_t)qi;
+                        state = (e - 1) * Q + (state >> 2);
+                    } else {
+                        o_mov[t] = 0; o_seq[t] = 0; o_q[t] = 0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = s; t < T; t += S) {
+            moves[(size_t)n * T + t] = o_mov[t];
+            seq[(size_t)n * T + t] = o_seq[t];
+            qual[(size_t)n * T + t] = o_q[t];
+        }
+    }
+}
+
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 template <int S>
@@ -275,7 +515,8 @@ int launch_decode(const __half* scores, int N, int T, float blank, float qscale,
         const size_t want = (size_t)atoi(pad) * 1024;
         if (want > dyn && want <= 200 * 1024) dyn = want;
     }
-    auto kern = crf_decode_kernel<S>;
+    const char* impl = getenv("B200_DECODE_IMPL");     // "v1": the original step loops; default: unrolled by two
+    auto kern = (impl && impl[0] == 'v' && impl[1] == '1') ? crf_decode_kernel<S> : crf_decode_kernel_v2<S>;
     B200_REQUIRE(dyn <= 200 * 1024, "crf_decode: chunk of %d frames needs %zu B of shared memory", T, dyn);
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     kern<<<N, S, dyn, stream>>>(scores, T, blank, qscale, qbias, beta, bsum, bp, pm, moves, seq, qual);

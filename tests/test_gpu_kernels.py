@@ -76,7 +76,14 @@ def test_gemm_overlapping_rows_and_row_remap(native, impl_name, tp, t_valid):
     assert err <= 4e-3, err
 
 
-def test_conv_stem_matches_oracle(native):
+@pytest.mark.parametrize("impl", ["tc", "fma"])
+def test_conv_stem_matches_oracle(native, impl, monkeypatch):
+    """Both stem kernels (mma.sync implicit GEMM for conv2 = default; CUDA-core FMA = B200_STEM_IMPL=fma) vs the oracle,
+    on a length that is not a multiple of the 256-position tile."""
+    if impl == "fma":
+        monkeypatch.setenv("B200_STEM_IMPL", "fma")
+    else:
+        monkeypatch.delenv("B200_STEM_IMPL", raising=False)
     spec = synth.model_spec("fast")
     w = synth.make_weights(spec, seed=9)
     n, L, padl = 3, 1000, 9
@@ -174,6 +181,20 @@ def test_crf_decode_matches_oracle(native, state_len, n, t):
     dq = np.abs(qual.cpu().numpy().astype(int) - o_qual.astype(int))
     assert dq.max() <= 1 and (dq != 0).mean() < 0.01
     assert o_moves.mean() > 0.2  # the case is not degenerate
+
+
+@pytest.mark.parametrize("state_len,n,t", [(3, 3, 7), (4, 5, 334), (4, 2, 1), (5, 2, 61)])
+def test_crf_decode_step_loop_variants_agree(native, state_len, n, t, monkeypatch):
+    """The default decode kernel (step loops unrolled by two) == the original loops (B200_DECODE_IMPL=v1), bit for bit,
+    for odd / even / single-frame chunks."""
+    from bonito_b200.engine import CrfDecoder
+    g = torch.Generator().manual_seed(state_len * 7 + t)
+    scores = (torch.randn(n, t, 4 ** (state_len + 1), generator=g) * 1.7).clamp(-5, 5).half().cuda()
+    new = [x.cpu() for x in CrfDecoder()(scores, state_len, blank_score=2.0, qscale=1.05, qbias=0.2)]
+    monkeypatch.setenv("B200_DECODE_IMPL", "v1")
+    old = [x.cpu() for x in CrfDecoder()(scores, state_len, blank_score=2.0, qscale=1.05, qbias=0.2)]
+    for a, b in zip(new, old):
+        assert torch.equal(a, b)
 
 
 def test_error_reporting(native):
