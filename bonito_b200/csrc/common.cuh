@@ -45,9 +45,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + exp2f(-1.4426950408889634f * x)); }
+// the bare SFU instruction: exp2f() wraps it in a rescaling path for results below 2^-126, which every use here adds to 1
+// (or multiplies into a sum that is >= 1), so flushing those to zero changes nothing
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_f(float x) {
-    return fmaf(2.0f, rcp_approx(1.0f + exp2f(-2.8853900817779268f * x)), -1.0f);
+    return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f);
 }
 
 __device__ __forceinline__ float swish_f(float x) { return x * sigmoid_f(x); }

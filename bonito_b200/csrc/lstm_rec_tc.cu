@@ -61,10 +61,10 @@ __device__ long long g_timeline[TL_STEPS][8];
 __device__ __forceinline__ void gate_activations(float ai, float af, float ag, float ao, float& si, float& sf, float& tg,
                                                  float& so) {
     constexpr float L = 1.4426950408889634f, CLAMP = 30.0f;
-    const float di = 1.0f + exp2f(fminf(-L * ai, CLAMP));
-    const float df = 1.0f + exp2f(fminf(-L * af, CLAMP));
-    const float dg = 1.0f + exp2f(fminf(-2.0f * L * ag, CLAMP));
-    const float dO = 1.0f + exp2f(fminf(-L * ao, CLAMP));
+    const float di = 1.0f + ex2_approx(fminf(-L * ai, CLAMP));
+    const float df = 1.0f + ex2_approx(fminf(-L * af, CLAMP));
+    const float dg = 1.0f + ex2_approx(fminf(-2.0f * L * ag, CLAMP));
+    const float dO = 1.0f + ex2_approx(fminf(-L * ao, CLAMP));
     const float pif = di * df, pgo = dg * dO;
     const float r = rcp_approx(pif * pgo);
     const float rif = r * pgo, rgo = r * pif;

@@ -284,7 +284,7 @@ attention_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cs, 
             float p[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                p[e] = exp2f((s[j][e] - msafe[e >> 1]) * scale_log2e);
+                p[e] = ex2_approx((s[j][e] - msafe[e >> 1]) * scale_log2e);
                 l_run[e >> 1] += p[e];
             }
             pf[j >> 1][(j & 1) * 2 + 0] = pack_h2(p[0], p[1]);
