@@ -123,7 +123,8 @@ swiglu_kernel(const __half* __restrict__ h, __half* __restrict__ out, long long 
 
 // ------------------------------------------------------------------------------------------------ attention
 // qkv [N][T][3][NH][64] fp16; rotary on q and k; keys j with q - wl <= j <= q + wr; out [N][T][NH*64].
-// One CTA = 64 queries of one (chunk, head), 4 warps x 16 query rows, flash-style online softmax over 64-key blocks.
+// One CTA = 64 queries of one (chunk, head), 4 warps x 16 query rows, flash-style online softmax over 64-key blocks
+// streamed through a cp.async double buffer.
 constexpr int HD = 64, AQ = 64, AK = 64, LDT = HD + 8;
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
@@ -204,12 +205,25 @@ __device__ __forceinline__ void load_tile(__half (*dst)[LDT], const __half* __re
     *reinterpret_cast<uint4*>(&dst[row][32 + half16 + 8]) = hi[1];
 }
 
+// the same tile through cp.async (16-byte pieces, rows outside [0, T) zero-filled): used for the double-buffered K / V stream
+__device__ __forceinline__ void load_tile_async(__half (*dst)[LDT], const __half* __restrict__ qkv, int n, int T, int NH,
+                                                int head, int which, int t0, int tid) {
+    const int row = tid >> 1, half16 = (tid & 1) * 16;
+    const int t = t0 + row;
+    const bool ok = t >= 0 && t < T;
+    const __half* src = ok ? qkv + ((((size_t)n * T + t) * 3 + which) * NH + head) * HD : qkv;
+    cp_async_16(&dst[row][half16], src + half16, ok);
+    cp_async_16(&dst[row][half16 + 8], src + half16 + 8, ok);
+    cp_async_16(&dst[row][32 + half16], src + 32 + half16, ok);
+    cp_async_16(&dst[row][32 + half16 + 8], src + 32 + half16 + 8, ok);
+}
+
 __global__ void __launch_bounds__(128)
 attention_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cs, __half* __restrict__ out, int T, int NH,
                  int wl, int wr, float scale_log2e) {
     __shared__ __align__(16) __half Qs[AQ][LDT];
-    __shared__ __align__(16) __half Ks[AK][LDT];
-    __shared__ __align__(16) __half Vs[AK][LDT];
+    __shared__ __align__(16) __half Kb[2][AK][LDT];   // double-buffered: block i+1 streams in while block i is consumed
+    __shared__ __align__(16) __half Vb[2][AK][LDT];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q0 = blockIdx.x * AQ, head = blockIdx.y, n = blockIdx.z;
     const int g = lane >> 2, qd = lane & 3;
@@ -230,11 +244,23 @@ attention_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cs, 
 
     int k_lo = q0 - wl; if (k_lo < 0) k_lo = 0;
     int k_hi = q0 + AQ - 1 + wr + 1; if (k_hi > T) k_hi = T;
-    for (int kb = (k_lo / AK) * AK; kb < k_hi; kb += AK) {
-        __syncthreads();   // previous block fully consumed
-        load_tile(Ks, qkv, cs, n, T, NH, head, 1, kb, tid);
-        load_tile(Vs, qkv, cs, n, T, NH, head, 2, kb, tid);
+    const int kb0 = (k_lo / AK) * AK;
+    if (kb0 < k_hi) {
+        load_tile_async(Kb[0], qkv, n, T, NH, head, 1, kb0, tid);
+        load_tile_async(Vb[0], qkv, n, T, NH, head, 2, kb0, tid);
+    }
+    cp_async_commit();
+    int buf = 0;
+    for (int kb = kb0; kb < k_hi; kb += AK, buf ^= 1) {
+        if (kb + AK < k_hi) {   // the other buffer was released by the barrier that ended the previous iteration
+            load_tile_async(Kb[buf ^ 1], qkv, n, T, NH, head, 1, kb + AK, tid);
+            load_tile_async(Vb[buf ^ 1], qkv, n, T, NH, head, 2, kb + AK, tid);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();   // everything but the group just committed: this block's tiles have landed
         __syncthreads();
+        __half (*Ks)[LDT] = Kb[buf];
+        __half (*Vs)[LDT] = Vb[buf];
         // S = Q K^T  (16 x 64 per warp)
         float s[8][4];
 #pragma unroll
@@ -270,7 +296,7 @@ attention_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cs, 
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             msafe[r] = (m_new[r] == -INFINITY) ? 0.f : m_new[r];
-            corr[r] = exp2f((m_run[r] - msafe[r]) * scale_log2e);   // exp2(-inf) = 0 for the first block
+            corr[r] = ex2_approx((m_run[r] - msafe[r]) * scale_log2e);   // ex2(-inf) = 0 for the first block
             m_run[r] = m_new[r];
             l_run[r] *= corr[r];
         }
@@ -303,6 +329,7 @@ attention_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cs, 
                 mma_16816(o[2 * dp + 1], pf[kk], b2, b3);
             }
         }
+        __syncthreads();   // this buffer is refilled by the loads issued at the top of the next iteration but one
     }
     // normalise and store
 #pragma unroll
