@@ -39,3 +39,19 @@ def test_native_path_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(native.NativeError, match="CUDA device"):
         native.require()
+
+
+def test_pipelined_scoring_refuses_cpu_models():
+    """No CPU fallback anywhere on the product path: the scoring loop behind basecall() raises on a CPU model."""
+    import pytest
+    import torch
+    from bonito_b200.crf.basecall import score_batches
+
+    class Dummy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.stride = 6
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        list(score_batches(Dummy(), iter([(0, torch.zeros(2, 1, 60))])))
