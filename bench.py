@@ -113,7 +113,7 @@ class ClockSampler:
 
 def build_model(device, rank, world):
     from bonito_b200.crf.model import Model
-    from oracle import synth
+    from bonito_b200 import synth
     spec = synth.model_spec(MODEL)
     weights = synth.make_weights(spec, seed=25)
     cfg = synth.model_config(spec, batchsize=BATCH, chunksize=CHUNK, overlap=500)
@@ -209,7 +209,7 @@ def main():
     import torch.distributed as dist
     from bonito_b200.crf.basecall import compute_scores
     from bonito_b200.decode import _decoder
-    from oracle import synth
+    from bonito_b200 import synth
 
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
@@ -340,7 +340,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{MODEL}-shaped LSTM-CRF (H={H}, {spec['n_lstm']} LSTM, {plan.n_scores} scores/frame), "
                                    f"batch {N}/GPU, {CHUNK}->{L}-sample chunks ({T} frames), forward+decode",
-                       "weights": "seeded synthetic (oracle/synth.py)", "l2": "per-step tensors (0.16-2.6 GB) exceed the 126 MB L2",
+                       "weights": "seeded synthetic (bonito_b200/synth.py)", "l2": "per-step tensors (0.16-2.6 GB) exceed the 126 MB L2",
                        "parallelism": f"chunk-sharded replicas x{world}"},
             "e2e": {"value": world * N * L * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": N * L * 2, "d2h_bytes_per_step": 3 * N * T, "ms_per_step": e2e_ms / args.steps,

@@ -3,7 +3,7 @@ import os, sys, json
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import synth
+from bonito_b200 import synth
 from bonito_b200.transformer import Model
 from bonito_b200.decode import _decoder
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256

@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import synth
+from bonito_b200 import synth
 from bonito_b200.crf.model import Model
 from bonito_b200.decode import beam_search
 spec = synth.model_spec("hac", n_lstm=5)

@@ -3,7 +3,7 @@ import sys, os
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", os.environ.get("CONN", "32"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
-from oracle import synth
+from bonito_b200 import synth
 from bonito_b200.decode import _decoder
 dev = torch.device("cuda", 0)
 model, spec, weights, chunksize = bench.build_model(dev, 0, 1)

@@ -18,7 +18,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from oracle import synth  # noqa: E402
+from bonito_b200 import synth  # noqa: E402
 
 
 def timed(fn, steps, warmup):

@@ -7,7 +7,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 dev = torch.device("cuda", 0)
 model, spec, weights, chunksize = bench.build_model(dev, 0, 1)
-from oracle import synth
+from bonito_b200 import synth
 from bonito_b200.decode import _decoder
 x = synth.squiggle(64, chunksize, seed=100).repeat(batch // 64 + 1, 1, 1)[:batch].to(dev, torch.float16)
 plan = model.native_plan(dev)
