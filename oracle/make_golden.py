@@ -10,6 +10,8 @@ Contents
                    get_stride, conv length table
   forward_sup.npz  narrow transformer through the reference's bonito.transformer classes (Triton / CUDA-only pieces
                    replaced by flash-attn's torch reference functions, see oracle/reference_shim.load_transformer)
+  forward_hac.npz  the headline shape (H = 384, 5 LSTM, k = 4) through the reference module tree, fp32 CPU: input, scores
+                   without the blank column [N,T,1024], decode_batch strings, digest of the seeded weights
   forward_fast.npz reference module tree (bonito.nn via from_dict, BatchNorm folded by fuse_bn_) forward in
                    fp32 on CPU: input, every parameter, per-layer features, scores [T,N,C+blanks];
                    + decode_batch strings (reference glue over the oracle's posteriors stand-in)
@@ -143,6 +145,40 @@ def forward_sup(ref):
     print("forward_sup.npz scores", tuple(scores.shape))
 
 
+def weights_digest(weights):
+    """sha256 over the fp16 bytes of every tensor (sorted by name): the fixture stores it instead of 12 MB of weights."""
+    import hashlib
+    h = hashlib.sha256()
+    for k in sorted(weights):
+        h.update(k.encode())
+        h.update(weights[k].numpy().astype(np.float16).tobytes())
+    return h.hexdigest()
+
+
+def forward_hac(ref):
+    """The headline shape (H = 384, 5 LSTM layers, 1024 scores) through the reference's module tree, fp32 on CPU.
+    Weights are `synth.make_weights(spec, seed=31)`: regenerated by the tests and compared by digest (the QR inside the
+    orthogonal init may round differently on another CPU; the tests then skip rather than compare apples with pears)."""
+    spec = synth.model_spec("hac")
+    cfg = synth.model_config(spec, batchnorm=False)
+    model = ref.crf_model.Model(cfg)
+    weights = synth.make_weights(spec, seed=31)
+    model.load_state_dict(synth.state_dict_from_weights(spec, weights))
+    model.eval()
+    x = synth.squiggle(2, 1200, seed=12).half().float()     # fp16-representable input: identical for every implementation
+    with torch.inference_mode():
+        scores = model.encoder(x)                            # [T, N, C + blanks]
+        strings = model.decode_batch(scores)
+    t, n, _ = scores.shape
+    s4 = scores.reshape(t, n, -1, 5)
+    assert torch.all(s4[..., 0] == 2.0)
+    ntc = s4[..., 1:].reshape(t, n, -1).permute(1, 0, 2).contiguous()
+    out = {"x": x.numpy().astype(np.float16), "scores_ntc": ntc.numpy(), "strings": np.array(json.dumps(strings)),
+           "digest": np.array(weights_digest(weights)), "seed": np.array(31), "stride": np.array(model.stride)}
+    np.savez_compressed(os.path.join(OUT, "forward_hac.npz"), **out)
+    print("forward_hac.npz scores", tuple(ntc.shape), "strings", [len(s) for s in strings], "max|s|", float(ntc.abs().max()))
+
+
 def get_stride_ok(ref, model):
     return ref.crf_model.get_stride(model.encoder) == 6 and model.stride == 6
 
@@ -153,6 +189,7 @@ def main():
     host_logic(ref)
     forward_fast(ref)
     forward_sup(ref)
+    forward_hac(ref)
 
 
 if __name__ == "__main__":

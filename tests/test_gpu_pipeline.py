@@ -1,4 +1,7 @@
 """GPU parity tests of the whole chunked forward + decode path against the CPU oracle."""
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -201,3 +204,32 @@ def test_score_batches_equals_compute_scores():
             assert torch.equal(res[name], want[name]), (key, name)
         assert int(res["moves"].sum()) > 10
     assert list(score_batches(model, iter([]))) == []
+
+
+def test_headline_shape_against_the_reference_fixture(golden_dir):
+    """hac shape through the native engine vs scores produced by the reference's own module tree (fp32 CPU,
+    tests/golden/forward_hac.npz): fp16 tolerance on the scores, same base sequences."""
+    from oracle.make_golden import weights_digest
+    from bonito_b200.crf.model import Model
+    from bonito_b200.decode import beam_search, to_str
+    gold = np.load(os.path.join(golden_dir, "forward_hac.npz"))
+    spec = synth.model_spec("hac")
+    weights = synth.make_weights(spec, seed=int(gold["seed"]))
+    if weights_digest(weights) != str(gold["digest"]):
+        pytest.skip("seeded hac weights round differently on this CPU: fixture not comparable")
+    model = Model(synth.model_config(spec, batchsize=8, chunksize=1200, overlap=0))
+    model.load_state_dict(synth.state_dict_from_weights(spec, weights))
+    model.use_koi(batchsize=8, chunksize=1200, quantize=False)
+    model = model.half().eval().cuda()
+    x = torch.from_numpy(gold["x"].astype(np.float16)).cuda()
+    with torch.inference_mode():
+        scores = model(x)
+        seq, _, _ = beam_search(scores)
+    ref = torch.from_numpy(gold["scores_ntc"])
+    err = (scores.float().cpu() - ref).abs()
+    print("vs reference fixture: max", err.max().item(), "mean", err.mean().item())
+    assert err.max().item() <= 2e-2 and err.mean().item() <= 2e-3
+    want = json.loads(str(gold["strings"]))
+    for got, w in zip([to_str(r) for r in seq], want):
+        same = sum(a == b for a, b in zip(got, w)) / max(len(w), 1)
+        assert abs(len(got) - len(w)) <= 2 and same >= 0.98, (len(got), len(w), same)

@@ -102,3 +102,25 @@ def test_c_decode_matches_numpy_oracle(gold):
         b = O.decode_native(sc, k)[:3]
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+def _hac_fixture(golden_dir):
+    from oracle.make_golden import weights_digest
+    gold = np.load(os.path.join(golden_dir, "forward_hac.npz"))
+    spec = synth.model_spec("hac")
+    weights = synth.make_weights(spec, seed=int(gold["seed"]))
+    if weights_digest(weights) != str(gold["digest"]):
+        pytest.skip("seeded hac weights round differently on this CPU (QR in the orthogonal init): fixture not comparable")
+    return gold, spec, weights
+
+
+def test_oracle_matches_reference_on_the_headline_shape(golden_dir):
+    """hac shape (H = 384, 5 LSTM layers, 1024 scores): oracle forward == the reference module tree's scores
+    (tests/golden/forward_hac.npz), oracle decode == the reference's decode_batch strings."""
+    gold, spec, weights = _hac_fixture(golden_dir)
+    x = torch.from_numpy(gold["x"].astype(np.float32))
+    with torch.no_grad():
+        s = O.lstm_crf_forward(weights, spec, x).permute(1, 0, 2).numpy()      # [N, T, C]
+    np.testing.assert_allclose(s, gold["scores_ntc"], atol=5e-5)
+    seq = build_ref.decode(gold["scores_ntc"], spec["state_len"], 2.0)[1]
+    assert [r[r != 0].tobytes().decode() for r in seq] == json.loads(str(gold["strings"]))
