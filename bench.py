@@ -301,8 +301,10 @@ def main():
         launches = {k: len(v) // args.steps for k, v in stage_ms.items()}
         step_ms = elapsed_ms / args.steps
         H = spec["hidden"]
-        n_tiles = -(-N // plan.TILE)
-        tile = min(plan.TILE, N)
+        tile_mode = bool(plan.tile) and os.environ.get("B200_LSTM_TILE", "1") != "0"
+        tile_chunks = plan.tile if tile_mode else plan.TILE
+        cluster = plan.tile_cs if tile_mode else 8
+        n_tiles = -(-N // tile_chunks)
         flops_step = {  # algorithmic FLOPs per step, all launches of the kernel
             "lstm_rec": spec["n_lstm"] * 2.0 * N * T * 4 * H * H,
             "lstm_in_gemm": spec["n_lstm"] * 2.0 * N * T * 4 * H * H,
@@ -314,8 +316,8 @@ def main():
         dominant = "lstm_rec"
         dur = per_step[dominant] / launches[dominant] * 1e-3
         ach = flops[dominant] / dur / 1e12
-        # one launch = one 8-CTA cluster (8 SMs) working on one tile-layer: compare with that share of the chip
-        launch_sms = 8 if launches[dominant] > spec["n_lstm"] else min(8 * n_tiles, sms)
+        # one launch = one cluster (6 or 8 SMs) working on one tile-layer, or all tiles of a layer: compare with that share of the chip
+        launch_sms = cluster if launches[dominant] > spec["n_lstm"] else min(cluster * n_tiles, sms)
         peak_share = peaks["tflops"] * launch_sms / sms
         chip_ach = flops_step[dominant] / (step_ms * 1e-3) / 1e12
         traffic = None
@@ -324,9 +326,10 @@ def main():
                 traffic = json.load(fh)["lstm_rec"]["bytes"] if N == BATCH else None
         except Exception:
             pass
-        roof = {"kernel": "lstm_rec_tc_kernel (persistent tcgen05 LSTM layer, one 8-CTA cluster per 32-chunk tile)",
+        roof = {"kernel": ("lstm_rec_tc6_kernel (persistent tcgen05 LSTM layer, one 6-CTA cluster per 48-chunk tile)" if tile_mode else
+                           "lstm_rec_tc_kernel (persistent tcgen05 LSTM layer, one 8-CTA cluster per 32-chunk tile)"),
                 "bound": "tensor", "achieved": ach, "peak": peak_share, "unit": "TFLOP/s", "frac": ach / peak_share,
-                "traffic": traffic, "traffic_algorithmic": 2.0 * T * min(plan.TILE, N) * 5 * H,
+                "traffic": traffic, "traffic_algorithmic": 2.0 * T * (N / launches[dominant] * spec["n_lstm"]) * 5 * H,
                 "peak_source": f"{peaks['source']} sustained bf16 GEMM {peaks['tflops']} TFLOP/s x {launch_sms}/{sms} SMs "
                                "(the share of the chip one launch occupies)",
                 "launch_ms": dur * 1e3, "launches_per_step": launches[dominant],

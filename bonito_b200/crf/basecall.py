@@ -153,10 +153,19 @@ def fmt(stride, attrs, rna=False):
     }
 
 
-def basecall(model, reads, chunksize=4000, overlap=100, batchsize=32, reverse=False, rna=False):
-    """Basecall an iterable of reads (objects with a float32 numpy `.signal`)."""
-    qscale = float(model.config.get("qscore", {}).get("scale", 1.0)) if hasattr(model, "config") else 1.0
-    qbias = float(model.config.get("qscore", {}).get("bias", 0.0)) if hasattr(model, "config") else 0.0
+def basecall(model, reads, chunksize=4000, overlap=100, batchsize=32, reverse=False, rna=False,
+             qscore_calibration=False):
+    """
+    Basecall an iterable of reads (objects with a float32 numpy `.signal`).
+
+    Like the reference (`bonito/crf/basecall.py:58-82`, which calls `compute_scores` with `reverse=` only) the quality
+    strings use scale 1.0 / offset 0.0.  `qscore_calibration=True` is an opt-in DEVIATION: it applies the `[qscore]`
+    scale / bias of the model config, which the reference's basecaller ignores.
+    """
+    qscale, qbias = 1.0, 0.0
+    if qscore_calibration and hasattr(model, "config"):
+        qscale = float(model.config.get("qscore", {}).get("scale", 1.0))
+        qbias = float(model.config.get("qscore", {}).get("bias", 0.0))
 
     chunks = thread_iter(
         ((read, 0, read.signal.shape[-1]), chunk(torch.from_numpy(read.signal), chunksize, overlap))

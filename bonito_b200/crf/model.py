@@ -116,6 +116,11 @@ class SeqdistModel(Module):
         reach the sm_100a kernels raises (no CPU fallback).
         """
         if self._native is None:
+            if x.is_cuda:
+                # the only CUDA path of this package is the native engine; an eager-torch forward here would be a silent
+                # non-native result with a different layout ([T, N, C+blanks])
+                raise RuntimeError("bonito_b200: CUDA model called without use_koi(); call model.use_koi(...) "
+                                   "(load_model(..., use_koi=True)) or run the module tree on the CPU")
             return self.encoder(x)
         return self.native_plan(x.device if x.is_cuda else None).forward(x)
 
@@ -145,6 +150,10 @@ class SeqdistModel(Module):
     def apply(self, fn):
         self._plan = None  # e.g. model.apply(fuse_bn_) rewrites the conv weights
         return super().apply(fn)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._plan = None  # the plan holds packed copies of the weights
+        return super().load_state_dict(*args, **kwargs)
 
     def use_koi(self, **kwargs):
         """Arm the B200 engine (the hook `_load_model` calls: bonito/util.py:292-296)."""

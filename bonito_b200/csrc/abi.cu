@@ -3,8 +3,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <mutex>
-
 #include "../../include/bonito_b200.h"
 #include "common.cuh"
 
@@ -25,18 +23,24 @@ bool lstm_rec_tc_supported(int hidden);
 int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
                        cudaStream_t stream);
 int launch_tmem_probe(float* out, cudaStream_t stream);
+int lstm_rec_tile_chunks(int hidden);
+int lstm_rec_tile_cluster(int hidden);
+int launch_lstm_rec_tc6(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
+                        cudaStream_t stream);
+int copy_lstm_timeline6(long long* host_out, int max_steps);
 int copy_lstm_timeline(long long* host_out, int max_steps);
 int lstm_rec_tc_max_clusters();
+int debug_max_clusters(int cluster_size, int threads, int smem_bytes);
 int launch_mma_bench(int ts_mode, int n, int iters, int chains, int blocks, long long* out, cudaStream_t stream);
 size_t crf_decode_workspace_bytes(int N, int T, int state_len);
 int launch_crf_decode(const __half* scores, int N, int T, int state_len, float blank, float qscale, float qbias,
                       void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream);
 
-static std::mutex g_err_mutex;
-static char g_err[1024] = "";
+// one message buffer per host thread: the reference drives this path from background threads (bonito/multiprocessing.py:118-122),
+// so a failing call must read back its own message, not another thread's
+static thread_local char g_err[1024] = "";
 
 void b200_set_error(const char* fmt, ...) {
-    std::lock_guard<std::mutex> lock(g_err_mutex);
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -64,16 +68,20 @@ int b200_gemm_fwd(const void* a, long long lda, const void* b, const void* bias,
                   int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
                   long long stride_inner, long long stride_outer, int impl, void* stream) {
     return b200_gemm_fwd_ex(a, lda, b, bias, c, ldc, m, n, k, act, lo, hi, rows_inner, valid_inner, stride_inner,
-                            stride_outer, impl, 0, stream);
+                            stride_outer, 0, 0, impl, 0, stream);
 }
 
 int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bias, void* c, long long ldc, int m,
                      int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
-                     long long stride_inner, long long stride_outer, int impl, int max_ctas, void* stream) {
+                     long long stride_inner, long long stride_outer, int cb_width, int cb_rows, int impl, int max_ctas,
+                     void* stream) {
     B200_REQUIRE(a && b && c, "gemm: null pointer argument");
     B200_REQUIRE(m >= 0 && n > 0 && k > 0 && rows_inner > 0, "gemm: bad sizes m=%d n=%d k=%d", m, n, k);
     B200_REQUIRE(k % 8 == 0 && lda % 8 == 0 && n % 8 == 0 && ldc % 8 == 0,
                  "gemm: k, lda, n, ldc must be multiples of 8 (k=%d lda=%lld n=%d ldc=%lld)", k, lda, n, ldc);
+    B200_REQUIRE(cb_width >= 0 && cb_rows >= 0 && cb_width % 32 == 0 && (cb_width == 0 || act != B200_ACT_SWIGLU),
+                 "gemm: column blocks must be multiples of 32 columns and cannot be combined with SwiGLU (cb_width=%d)",
+                 cb_width);
     if (act == B200_ACT_SWIGLU)
         B200_REQUIRE(n % 64 == 0 && !bias && impl != B200_GEMM_MMA_SYNC,
                      "gemm: the fused SwiGLU epilogue needs n %% 64 == 0, no bias and the tcgen05 path (n=%d)", n);
@@ -87,6 +95,8 @@ int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bi
     ep.map.valid_inner = valid_inner;
     ep.map.stride_inner = stride_inner;
     ep.map.stride_outer = stride_outer;
+    ep.cb_width = cb_width;
+    ep.cb_rows = cb_rows;
     if (impl == B200_GEMM_AUTO) {
         const char* env = getenv("B200_GEMM_IMPL");
         impl = (env && strcmp(env, "mma") == 0 && act != B200_ACT_SWIGLU) ? B200_GEMM_MMA_SYNC : B200_GEMM_TCGEN05;
@@ -146,12 +156,34 @@ int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, in
                            (cudaStream_t)stream);
 }
 
+int b200_lstm_tile_chunks(int hidden) { return lstm_rec_tile_chunks(hidden); }
+
+int b200_lstm_tile_cluster(int hidden) { return lstm_rec_tile_cluster(hidden); }
+
+int b200_lstm_rec_tile_fwd(const void* gx, const void* whh, void* y, int t, int n, int hidden, int reverse,
+                           void* stream) {
+    B200_REQUIRE(gx && whh && y, "lstm_rec_tile: null pointer argument");
+    B200_REQUIRE(t >= 0 && n >= 0, "lstm_rec_tile: bad sizes t=%d n=%d", t, n);
+    if (t == 0 || n == 0) return 0;
+    return launch_lstm_rec_tc6((const __half*)gx, (const __half*)whh, (__half*)y, t, n, hidden, reverse,
+                               (cudaStream_t)stream);
+}
+
+int b200_debug_lstm_tile_timeline(long long* host_out, int max_steps) {
+    B200_REQUIRE(host_out != nullptr && max_steps > 0, "lstm_tile_timeline: bad arguments");
+    return copy_lstm_timeline6(host_out, max_steps);
+}
+
 int b200_debug_tmem_probe(void* out, void* stream) {
     B200_REQUIRE(out != nullptr, "tmem_probe: null pointer argument");
     return launch_tmem_probe((float*)out, (cudaStream_t)stream);
 }
 
 int b200_debug_lstm_max_clusters(void) { return lstm_rec_tc_max_clusters(); }
+
+int b200_debug_max_clusters(int cluster_size, int threads, int smem_bytes) {
+    return debug_max_clusters(cluster_size, threads, smem_bytes);
+}
 
 int b200_debug_lstm_timeline(long long* host_out, int max_steps) {
     B200_REQUIRE(host_out != nullptr && max_steps > 0, "lstm_timeline: bad arguments");

@@ -125,6 +125,9 @@ struct GemmEpilogue {
     int act;             // B200_ACT_*
     float lo, hi;        // clamp bounds
     RowMap map;
+    // column blocks: output column c of mapped row R goes to row R + (c / cb_width) * cb_rows, column c % cb_width
+    // (cb_width = 0: off).  Used to write the LSTM input projection as [t][cluster rank][chunk][256 columns].
+    int cb_width, cb_rows;
 };
 
 // Host-side launchers (defined in the .cu files, used by abi.cu)

@@ -55,7 +55,43 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int ts_mode, int n, i
     if (warp == 0) tc_dealloc(tb, 512);
 }
 
+// dummy cluster kernel for occupancy queries
+__global__ void cluster_probe_kernel(int* out) {
+    extern __shared__ unsigned char smem_raw[];
+    if (threadIdx.x == 0 && out != nullptr) atomicAdd(out, (int)cluster_ctarank() + (smem_raw[0] & 0));
+}
+
 }  // namespace
+
+// how many clusters of `cluster_size` CTAs (threads, dynamic shared memory as given) the device holds at once
+int debug_max_clusters(int cluster_size, int threads, int smem_bytes) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size * 64);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaFuncSetAttribute(cluster_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    if (cluster_size > 8 &&
+        cudaFuncSetAttribute(cluster_probe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, cluster_probe_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return n;
+}
 
 int launch_mma_bench(int ts_mode, int n, int iters, int chains, int blocks, long long* out, cudaStream_t stream) {
     const int smem = 16384 + 32768 + 1024;

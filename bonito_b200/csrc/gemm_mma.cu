@@ -114,7 +114,14 @@ gemm_mma_kernel(const __half* __restrict__ A, long long lda, const __half* __res
                 }
                 v0 = apply_act_f16(v0, ep.act, ep.lo, ep.hi);
                 v1 = apply_act_f16(v1, ep.act, ep.lo, ep.hi);
-                __half* dst = C + orow * ldc + gn;
+                long long drow = orow;
+                int dcol = gn;
+                if (ep.cb_width > 0) {   // column-block remap (cb_width is even: a pair never straddles two blocks)
+                    const int cb = gn / ep.cb_width;
+                    drow += (long long)cb * ep.cb_rows;
+                    dcol = gn - cb * ep.cb_width;
+                }
+                __half* dst = C + drow * ldc + dcol;
                 if (gn + 1 < N) {
                     *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(v0, v1);
                 } else {

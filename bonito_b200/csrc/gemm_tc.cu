@@ -81,12 +81,20 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* 
         __syncwarp();
         const int chunk = lane & 3;
         const bool col_ok = gcol + chunk * 8 < ncols;   // widths are multiples of 8
+        // column-block remap (cb_width is a multiple of 32, so a 32-column block never straddles two column blocks)
+        long long row_add = 0;
+        int ocol = gcol;
+        if (ep.cb_width > 0) {
+            const int cb = gcol / ep.cb_width;
+            row_add = (long long)cb * ep.cb_rows;
+            ocol = gcol - cb * ep.cb_width;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int row = 8 * i + (lane >> 2);
             const long long r = __shfl_sync(0xffffffffu, orow, row);
             const uint4 val = *reinterpret_cast<const uint4*>(tbuf + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
-            if (r >= 0 && col_ok) *reinterpret_cast<uint4*>(C + r * ldc + gcol + chunk * 8) = val;
+            if (r >= 0 && col_ok) *reinterpret_cast<uint4*>(C + (r + row_add) * ldc + ocol + chunk * 8) = val;
         }
         __syncwarp();
     };

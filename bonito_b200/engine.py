@@ -142,6 +142,9 @@ class LstmCrfPlan:
         H = self.hidden
         if native.lstm_cluster_size(H) == 0:
             raise UnsupportedModel(f"LSTM hidden size {H} has no native kernel")
+        # H = 384: second-generation recurrent kernel (48-chunk tiles, 6-CTA clusters, gx streamed through shared memory)
+        self.tile = native.lstm_tile_chunks(H)            # 0: only the generic-layout kernel exists for this width
+        self.tile_cs = native.lstm_tile_cluster(H)
         unit = torch.arange(H)
         perm_ih = (torch.arange(4)[None, :] * H + unit[:, None]).reshape(-1)          # [unit][gate]
         perm_hh = (torch.arange(H // 8)[:, None, None] * 8 + torch.arange(4)[None, :, None] * H
@@ -334,14 +337,159 @@ class LstmCrfPlan:
             DECODE_CACHE.put(out, (self.state_len, self.blank_score, float(decode[0]), float(decode[1])), tuple(dec))
         return out
 
+    # ------------------------------------------------------------------------------------------
+    # tile layout (H = 384): activations [tile][T][48][H], gate pre-activations [tile][T][6][48][256]
+    # ------------------------------------------------------------------------------------------
+    def _tile_layout_buffers(self, N, L, slot=0):
+        key = ("tiles", N, L, slot)
+        if key not in self._bufs:
+            for k in [k for k in self._bufs if k[0] != "tiles" or k[1:3] != (N, L)]:
+                del self._bufs[k]
+            T = self.frames(L)
+            need = max(self.pad3 + L, (T - 1) * self.s3 + self.k3)
+            Tp = -(-need // self.s3)
+            Lp = Tp * self.s3
+            dev, f16, H, TB = self.device, torch.float16, self.hidden, self.tile
+            nt = -(-N // TB)
+            tail = self.k3 * self.c2
+            stem = torch.empty(N * Lp * self.c2 + tail, dtype=f16, device=dev)
+            stem[-tail:].zero_()
+            self._bufs[key] = dict(
+                T=T, Tp=Tp, Lp=Lp, nt=nt, stem=stem,
+                # zero-filled once: rows of chunks beyond the batch (last tile) are never written and must stay finite
+                ya=torch.zeros(nt, T, TB, H, dtype=f16, device=dev),
+                yb=torch.zeros(nt, T, TB, H, dtype=f16, device=dev),
+                gx=torch.zeros(nt, T, self.tile_cs, TB, 4 * H // self.tile_cs, dtype=f16, device=dev),
+                streams=[torch.cuda.Stream(device=dev) for _ in range(nt)],
+                rec_streams=[torch.cuda.Stream(device=dev, priority=-1) for _ in range(nt)],   # high priority
+                rec_ready=[torch.cuda.Event() for _ in range(nt)], rec_done=[torch.cuda.Event() for _ in range(nt)],
+                done=[torch.cuda.Event() for _ in range(nt)],
+                start=torch.cuda.Event(),
+            )
+        return self._bufs[key]
+
+    def forward_tiles(self, x, out=None, gemm_impl=native.GEMM_AUTO, events=None, return_features=False, streams=False,
+                      slot=0):
+        """
+        Forward in the tile layout.  `streams=False`: layer by layer on the current stream -- one input-projection GEMM
+        and ONE recurrent launch (a cluster per tile, all in one wave) per layer.  `streams=True`: every tile gets its own
+        stream (conv GEMM -> 5 x (input GEMM -> recurrent cluster) -> CRF GEMM), recurrent launches on high-priority side
+        streams, so the GEMMs of one tile fill the SMs the other tiles' clusters leave free.  Bit-identical results.
+        `slot` selects one of several independent buffer sets (batches in flight at the same time).
+        """
+        import os
+        if x.dim() == 3:
+            x = x[:, 0, :]
+        x = x.to(device=self.device, dtype=torch.float16).contiguous()
+        N, L = x.shape
+        H, TB, CS = self.hidden, self.tile, self.tile_cs
+        CW = 4 * H // CS                     # gx columns per cluster rank (256)
+        b = self._tile_layout_buffers(N, L, slot)
+        T, Tp, Lp, nt = b["T"], b["Tp"], b["Lp"], b["nt"]
+        if out is None:
+            out = torch.empty(N, T, self.n_scores, dtype=torch.float16, device=self.device)
+        main = torch.cuda.current_stream()
+        feats = {}
+        cap = int(os.environ.get("B200_TILE_GEMM_CTAS", self.TILE_GEMM_CTAS))
+
+        def staged(name, st):
+            return _StreamStage(name, events, st)
+
+        def conv_gemm(i, st):       # rows r = i_chunk*Tp + t of tile i -> ya[i][t][i_chunk]
+            n0 = i * TB
+            nb = min(TB, N - n0)
+            with staged("conv_gemm", st):
+                native.gemm(b["stem"][n0 * Lp * self.c2:], self.s3 * self.c2, self.w3, self.b3, b["ya"][i], H, nb * Tp, H,
+                            self.k3 * self.c2, act=self.act3, rows_inner=Tp, valid_inner=T, stride_inner=TB,
+                            stride_outer=1, impl=gemm_impl, stream=st)
+
+        def in_gemm(src, layer, tiles, st, max_ctas=0):      # rows (tile, t, chunk) -> gx[tile][t][rank][chunk][CW]
+            i0, cnt = tiles
+            with staged("lstm_in_gemm", st):
+                native.gemm(src[i0], H, layer["wih"], layer["bias"], b["gx"][i0], CW, cnt * T * TB, 4 * H, H,
+                            rows_inner=TB, valid_inner=TB, stride_inner=1, stride_outer=CS * TB, cb_width=CW, cb_rows=TB,
+                            impl=gemm_impl, stream=st, max_ctas=max_ctas)
+
+        def rec(dst, layer, tiles, st):
+            i0, cnt = tiles
+            n = min(cnt * TB, N - i0 * TB)
+            with staged("lstm_rec", st):
+                native.lstm_rec_tile(b["gx"][i0], layer["whh"], dst[i0], T, n, H, layer["reverse"], stream=st)
+
+        def crf_gemm(src, i, st, max_ctas=0):   # rows r = t*TB + i_chunk of tile i -> out[n0 + i_chunk][t]
+            n0 = i * TB
+            nb = min(TB, N - n0)
+            with staged("crf_gemm", st):
+                native.gemm(src[i], H, self.wl, self.bl, out[n0:], self.n_scores, T * TB, self.n_scores, H,
+                            act=self.act_l, lo=self.lo, hi=self.hi, rows_inner=TB, valid_inner=nb, stride_inner=T,
+                            stride_outer=1, impl=gemm_impl, stream=st, max_ctas=max_ctas)
+
+        def gather(buf):            # [tile][T][48][H] -> [T][N][H]
+            return buf.permute(1, 0, 2, 3).reshape(T, nt * TB, H)[:, :N].clone()
+
+        with _StreamStage("conv_stem", events, main):
+            native.conv_stem(x, self.w1, self.b1, self.act1, self.w2, self.b2, self.act2, b["stem"], Lp, self.pad3)
+        if return_features:
+            feats["stem"] = b["stem"][:N * Lp * self.c2].view(N, Lp, self.c2)[:, self.pad3:self.pad3 + L].clone()
+        cur, nxt = b["ya"], b["yb"]
+
+        if not streams:
+            for i in range(nt):
+                conv_gemm(i, main)
+            if return_features:
+                feats["conv"] = gather(cur)
+            for li, layer in enumerate(self.lstm):
+                in_gemm(cur, layer, (0, nt), main)
+                rec(nxt, layer, (0, nt), main)
+                cur, nxt = nxt, cur
+                if return_features:
+                    feats[f"lstm{li}"] = gather(cur)
+            for i in range(nt):
+                crf_gemm(cur, i, main)
+            return (out, feats) if return_features else out
+
+        b["start"].record(main)
+        for i in range(nt):
+            st = b["streams"][i]
+            st.wait_event(b["start"])
+            conv_gemm(i, st)
+        for li, layer in enumerate(self.lstm):
+            for i in range(nt):
+                st, rs = b["streams"][i], b["rec_streams"][i]
+                in_gemm(cur, layer, (i, 1), st, max_ctas=cap if li > 0 else 0)
+                b["rec_ready"][i].record(st)
+                rs.wait_event(b["rec_ready"][i])
+                rec(nxt, layer, (i, 1), rs)
+                b["rec_done"][i].record(rs)
+                st.wait_event(b["rec_done"][i])
+            cur, nxt = nxt, cur
+        for i in range(nt):
+            st = b["streams"][i]
+            crf_gemm(cur, i, st, max_ctas=cap)
+            b["done"][i].record(st)
+            main.wait_event(b["done"][i])
+        return out
+
     def forward(self, x, out=None, gemm_impl=native.GEMM_AUTO, return_features=False, events=None, tiled=None,
                 decode=None):
+        with torch.cuda.device(self.device):    # streams / events / launches belong to the plan's device, whatever is current
+            return self._forward(x, out=out, gemm_impl=gemm_impl, return_features=return_features, events=events,
+                                 tiled=tiled, decode=decode)
+
+    def _forward(self, x, out=None, gemm_impl=native.GEMM_AUTO, return_features=False, events=None, tiled=None,
+                 decode=None):
         """
         x: [N, 1, L] (or [N, L]) fp16 CUDA -> scores [N, T, C] fp16 (no blank column).
         `events`: optional list; (stage, start, end) CUDA events are appended per kernel.
         `tiled`: run the tile-pipelined schedule (default: whenever the batch has more than one 32-chunk tile).
         `decode`: see `forward_tiled` (ignored by the single-stream schedule).
         """
+        import os
+        if self.tile and os.environ.get("B200_LSTM_TILE", "1") != "0":
+            if tiled is None:
+                tiled = (not return_features) and x.shape[0] > self.tile and os.environ.get("B200_TILE_STREAMS", "1") != "0"
+            return self.forward_tiles(x, out=out, gemm_impl=gemm_impl, events=events, return_features=return_features,
+                                      streams=tiled)
         if tiled is None:
             tiled = (not return_features) and x.shape[0] > self.TILE
         if tiled:
@@ -426,9 +574,13 @@ class CrfDecoder:
     """Workspace-caching wrapper around b200_crf_decode."""
 
     def __init__(self):
-        self._ws = None
+        self._ws_by_device = {}     # one workspace per (device, host thread): basecall() decodes on background threads
 
     def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0, events=None, out=None):
+        with torch.cuda.device(scores.device):
+            return self._call(scores, state_len, blank_score, qscale, qbias, events, out)
+
+    def _call(self, scores, state_len, blank_score, qscale, qbias, events, out):
         """-> (moves, sequence, qstring) uint8 [N, T] on the device; `out`: optional uint8 [3, N, T] to write them into."""
         n, t, c = scores.shape
         if c != 4 ** (state_len + 1):
@@ -442,9 +594,12 @@ class CrfDecoder:
             return cached
         scores = scores.to(torch.float16).contiguous()
         need = native.crf_decode_workspace_bytes(n, t, state_len)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != scores.device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=scores.device)
+        import threading
+        key = (scores.device, threading.get_ident())
+        ws = self._ws_by_device.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._ws_by_device[key] = torch.empty(need, dtype=torch.uint8, device=scores.device)
         outs = list(out) if out is not None else [torch.empty(n, t, dtype=torch.uint8, device=scores.device) for _ in range(3)]
         with _Stage("crf_decode", events):
-            native.crf_decode(scores, state_len, blank_score, qscale, qbias, self._ws, *outs)
+            native.crf_decode(scores, state_len, blank_score, qscale, qbias, ws, *outs)
         return tuple(outs)  # moves, sequence, qstring

@@ -144,6 +144,10 @@ class TransformerPlan:
         return self._bufs[key]
 
     def forward(self, x, out=None, events=None, return_features=False, **_):
+        with torch.cuda.device(self.device):    # streams / events / launches belong to the plan's device, whatever is current
+            return self._forward(x, out=out, events=events, return_features=return_features)
+
+    def _forward(self, x, out=None, events=None, return_features=False):
         if x.dim() == 3:
             x = x[:, 0, :]
         x = x.to(device=self.device, dtype=torch.float16).contiguous()

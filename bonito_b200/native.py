@@ -27,7 +27,8 @@ SIGNATURES = {
     "b200_gemm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                               c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_void_p]),
     "b200_gemm_fwd_ex": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
-                                 c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_void_p]),
+                                 c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
     "b200_conv_first_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                     c_int, c_void_p]),
     "b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -36,9 +37,14 @@ SIGNATURES = {
     "b200_swiglu_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "b200_lstm_cluster_size": (c_int, [c_int]),
     "b200_lstm_rec_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200_lstm_tile_chunks": (c_int, [c_int]),
+    "b200_lstm_tile_cluster": (c_int, [c_int]),
+    "b200_lstm_rec_tile_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200_debug_lstm_tile_timeline": (c_int, [c_void_p, c_int]),
     "b200_debug_tmem_probe": (c_int, [c_void_p, c_void_p]),
     "b200_debug_lstm_timeline": (c_int, [c_void_p, c_int]),
     "b200_debug_lstm_max_clusters": (c_int, []),
+    "b200_debug_max_clusters": (c_int, [c_int, c_int, c_int]),
     "b200_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_crf_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
@@ -117,15 +123,17 @@ def conv_stem(x, w1, b1, act1, w2, b2, act2, out, lp, padl):
 
 
 def gemm(a_ptr_tensor, lda, b, bias, c, ldc, m, n, k, act=ACT_NONE, lo=0.0, hi=0.0,
-         rows_inner=None, valid_inner=None, stride_inner=1, stride_outer=0, impl=GEMM_AUTO, stream=None, max_ctas=0):
-    """C = act(A B^T + bias); `a_ptr_tensor` / `c` only supply base pointers (rows may overlap / be remapped)."""
+         rows_inner=None, valid_inner=None, stride_inner=1, stride_outer=0, impl=GEMM_AUTO, stream=None, max_ctas=0,
+         cb_width=0, cb_rows=0):
+    """C = act(A B^T + bias); `a_ptr_tensor` / `c` only supply base pointers (rows may overlap / be remapped; `cb_*`:
+    column blocks, see b200_gemm_fwd_ex)."""
     lib = require()
     if rows_inner is None:
         rows_inner, valid_inner = m, m
     with torch.cuda.device(c.device):
         rc = lib.b200_gemm_fwd_ex(_ptr(a_ptr_tensor), lda, _ptr(_f16(b, "b")), _ptr(bias), _ptr(c), ldc, m, n, k,
                                   act, float(lo), float(hi), rows_inner, valid_inner, stride_inner, stride_outer,
-                                  impl, int(max_ctas), _stream(stream))
+                                  int(cb_width), int(cb_rows), impl, int(max_ctas), _stream(stream))
     _check(rc, "b200_gemm_fwd")
     return c
 
@@ -135,31 +143,35 @@ def conv_first(x, w, bias, act, out, lp, padl, stream=None):
     lib = require()
     n, l = x.shape
     c, _, k = w.shape
-    rc = lib.b200_conv_first_fwd(_ptr(_f16(x, "x")), n, l, c, k, _ptr(_f16(w, "w")), _ptr(bias), act, _ptr(out), lp, padl,
-                                 _stream(stream))
+    with torch.cuda.device(out.device):
+        rc = lib.b200_conv_first_fwd(_ptr(_f16(x, "x")), n, l, c, k, _ptr(_f16(w, "w")), _ptr(bias), act, _ptr(out), lp,
+                                     padl, _stream(stream))
     _check(rc, "b200_conv_first_fwd")
     return out
 
 
 def attention(qkv, cos_sin, out, n, t, heads, head_dim, wl, wr, stream=None):
     lib = require()
-    rc = lib.b200_attention_fwd(_ptr(_f16(qkv, "qkv")), _ptr(_f16(cos_sin, "cos_sin")), _ptr(out), n, t, heads, head_dim,
-                                wl, wr, _stream(stream))
+    with torch.cuda.device(out.device):
+        rc = lib.b200_attention_fwd(_ptr(_f16(qkv, "qkv")), _ptr(_f16(cos_sin, "cos_sin")), _ptr(out), n, t, heads,
+                                    head_dim, wl, wr, _stream(stream))
     _check(rc, "b200_attention_fwd")
     return out
 
 
 def rmsnorm_residual(a, x, w, alpha, eps, out, m, d, stream=None):
     lib = require()
-    rc = lib.b200_rmsnorm_residual_fwd(_ptr(_f16(a, "a")), _ptr(_f16(x, "x")), _ptr(_f16(w, "w")), float(alpha), float(eps),
-                                       _ptr(out), m, d, _stream(stream))
+    with torch.cuda.device(out.device):
+        rc = lib.b200_rmsnorm_residual_fwd(_ptr(_f16(a, "a")), _ptr(_f16(x, "x")), _ptr(_f16(w, "w")), float(alpha),
+                                           float(eps), _ptr(out), m, d, _stream(stream))
     _check(rc, "b200_rmsnorm_residual_fwd")
     return out
 
 
 def swiglu(h, out, m, f, stream=None):
     lib = require()
-    rc = lib.b200_swiglu_fwd(_ptr(_f16(h, "h")), _ptr(out), m, f, _stream(stream))
+    with torch.cuda.device(out.device):
+        rc = lib.b200_swiglu_fwd(_ptr(_f16(h, "h")), _ptr(out), m, f, _stream(stream))
     _check(rc, "b200_swiglu_fwd")
     return out
 
@@ -175,6 +187,35 @@ def lstm_rec(gx, whh, y, t, n, hidden, reverse, stream=None):
                                    int(bool(reverse)), _stream(stream))
     _check(rc, "b200_lstm_rec_fwd")
     return y
+
+
+def lstm_tile_chunks(hidden):
+    """Chunks per tile of the tile-layout recurrent kernel (0: this hidden size only has the generic-layout kernel)."""
+    return load().b200_lstm_tile_chunks(hidden)
+
+
+def lstm_tile_cluster(hidden):
+    return load().b200_lstm_tile_cluster(hidden)
+
+
+def lstm_rec_tile(gx, whh, y, t, n, hidden, reverse, stream=None):
+    """gx [tiles][T][6][48][256], y [tiles][T][48][H] (see b200_lstm_rec_tile_fwd); n chunks = ceil(n/48) tiles."""
+    lib = require()
+    with torch.cuda.device(y.device):
+        rc = lib.b200_lstm_rec_tile_fwd(_ptr(gx), _ptr(_f16(whh, "whh")), _ptr(y), t, n, hidden,
+                                        int(bool(reverse)), _stream(stream))
+    _check(rc, "b200_lstm_rec_tile_fwd")
+    return y
+
+
+def lstm_tile_timeline(steps=256):
+    """[steps, 8] int64 SM-clock stamps recorded by CTA 0 of the last lstm_rec_tile launch under B200_LSTM_DEBUG=3."""
+    import numpy as np
+    buf = np.zeros((steps, 8), dtype=np.int64)
+    n = load().b200_debug_lstm_tile_timeline(buf.ctypes.data_as(c_void_p), steps)
+    if n < 0:
+        _check(n, "b200_debug_lstm_tile_timeline")
+    return buf[:n]
 
 
 def tmem_probe():

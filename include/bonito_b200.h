@@ -46,7 +46,8 @@ extern "C" {
 /* Library version (major*10000 + minor*100 + patch). */
 int b200_version(void);
 
-/* Message of the last failure on any thread ("" if none). */
+/* Message of the last failure ON THE CALLING THREAD ("" if none); the buffer is thread-local and stays valid until the
+ * same thread fails again. */
 const char* b200_last_error(void);
 
 /*
@@ -73,13 +74,17 @@ int b200_gemm_fwd(const void* a, long long lda, const void* b, const void* bias,
                   long long stride_inner, long long stride_outer, int impl, void* stream);
 
 /*
- * Same, with a cap on the number of (persistent) CTAs the tcgen05 kernel may occupy (0 = every SM).  The tile-pipelined
- * engine caps the GEMMs it runs next to resident recurrent clusters, so that they trickle through the free SMs instead
- * of flooding the machine and holding back the next cluster launch.
+ * Same, with
+ *   max_ctas  a cap on the number of (persistent) CTAs the tcgen05 kernel may occupy (0 = every SM): the tile-pipelined
+ *             engine caps the GEMMs it runs next to resident recurrent clusters;
+ *   cb_width, cb_rows  column blocks (cb_width = 0: off; multiple of 32): output column c of mapped row R is written to
+ *             row R + (c / cb_width) * cb_rows, column c % cb_width.  With ldc = cb_width this lays the LSTM input
+ *             projection out as [t][cluster rank][chunk][cb_width], one contiguous block per recurrent CTA and step.
  */
 int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bias, void* c, long long ldc, int m,
                      int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
-                     long long stride_inner, long long stride_outer, int impl, int max_ctas, void* stream);
+                     long long stride_inner, long long stride_outer, int cb_width, int cb_rows, int impl, int max_ctas,
+                     void* stream);
 
 /*
  * Cluster size the packed LSTM operands must be laid out for (0: hidden size unsupported).
@@ -99,6 +104,25 @@ int b200_lstm_cluster_size(int hidden);
  */
 int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, int hidden, int reverse,
                       void* stream);
+
+/*
+ * Tile layout of the H = 384 recurrent kernel (second generation: clusters of 6 CTAs x 64 hidden units, three interleaved
+ * 16-chunk sub-tiles, input projection streamed through shared memory by cp.async.bulk).
+ *   b200_lstm_tile_chunks(hidden)   chunks per tile (48 for hidden = 384; 0 = this hidden size has no tile kernel)
+ *   b200_lstm_tile_cluster(hidden)  CTAs per cluster = column blocks of gx (6)
+ *   gx  [tiles][T][6][48][256]  columns of cluster rank r: [unit/8 - 8r][unit%8][gate i,f,g,o]  (b200_gemm_fwd_ex with
+ *                               rows (t, chunk), cb_width = 256, cb_rows = 48, ldc = 256)
+ *   whh [4H][H]                 as for b200_lstm_rec_fwd
+ *   y   [tiles][T][48][H]       h_t in natural unit order; rows of chunks >= n are not written
+ * tiles = ceil(n / 48); one launch runs all of them (one cluster each; 22 fit on a B200 at once).
+ */
+int b200_lstm_tile_chunks(int hidden);
+int b200_lstm_tile_cluster(int hidden);
+int b200_lstm_rec_tile_fwd(const void* gx, const void* whh, void* y, int t, int n, int hidden, int reverse,
+                           void* stream);
+
+/* Timing aid: as b200_debug_lstm_timeline, for b200_lstm_rec_tile_fwd. */
+int b200_debug_lstm_tile_timeline(long long* host_out, int max_steps);
 
 /*
  * ---- transformer (sup) path: bonito/transformer/model.py ----
@@ -134,6 +158,10 @@ int b200_debug_tmem_probe(void* out, void* stream);
 
 /* Number of 8-CTA clusters of the tcgen05 recurrent kernel the current device can hold at once (-1 on error). */
 int b200_debug_lstm_max_clusters(void);
+
+/* Occupancy query: clusters of `cluster_size` CTAs (`threads` threads, `smem_bytes` dynamic shared memory, one CTA per SM
+ * when smem_bytes > half an SM) the current device holds at once; -1 on error.  GPC packing decides (B200: 148 SMs). */
+int b200_debug_max_clusters(int cluster_size, int threads, int smem_bytes);
 
 /*
  * Timing aid: after a b200_lstm_rec_fwd launched with B200_LSTM_DEBUG=3 in the environment, copies the SM-clock

@@ -127,6 +127,68 @@ def test_lstm_layer_matches_oracle(native, hidden, n, t, reverse):
     assert err <= 5e-3, err
 
 
+@pytest.mark.parametrize("impl_name", ["tcgen05", "mma"])
+def test_gemm_column_blocks(native, impl_name):
+    """cb_width / cb_rows: the layout the tile recurrent kernel reads, [t][rank][chunk][256] from rows (t, chunk)."""
+    impl = native.GEMM_TCGEN05 if impl_name == "tcgen05" else native.GEMM_MMA_SYNC
+    t, tb, cs, cw, k = 37, 48, 6, 256, 384
+    g = torch.Generator().manual_seed(11)
+    a = _dev(torch.randn(t * tb, k, generator=g))
+    w = _dev(torch.randn(cs * cw, k, generator=g) / k ** 0.5)
+    bias = _dev(torch.randn(cs * cw, generator=g))
+    out = torch.full((t, cs, tb, cw), float("nan"), dtype=torch.float16, device="cuda")
+    native.gemm(a, k, w, bias, out, cw, t * tb, cs * cw, k, rows_inner=tb, valid_inner=tb, stride_inner=1,
+                stride_outer=cs * tb, cb_width=cw, cb_rows=tb, impl=impl)
+    torch.cuda.synchronize()
+    ref = _ref_gemm(a.cpu(), w.cpu(), bias.cpu()).view(t, tb, cs, cw).permute(0, 2, 1, 3)
+    assert not torch.isnan(out).any()
+    assert (out.float().cpu() - ref).abs().max().item() <= 4e-3
+
+
+@pytest.mark.parametrize("n,t,reverse", [(5, 30, False), (16, 1, True), (17, 2, False), (48, 3, True), (50, 31, False),
+                                         (100, 12, True), (96, 40, False), (33, 9, True)])
+def test_lstm_tile_kernel_matches_oracle(native, n, t, reverse):
+    """Second-generation H=384 recurrent kernel (6-CTA clusters, 48-chunk tiles, gx through the shared-memory ring): whole,
+    partial and multiple tiles, 1..3 active sub-tiles, T below / above the ring depth, both directions."""
+    H = 384
+    tb, cs = native.lstm_tile_chunks(H), native.lstm_tile_cluster(H)
+    assert (tb, cs) == (48, 6)
+    cw = 4 * H // cs
+    nt = -(-n // tb)
+    g = torch.Generator().manual_seed(1000 + n + t)
+    x = (torch.randn(t, n, H, generator=g) * 0.5).half()
+    w_ih = (torch.randn(4 * H, H, generator=g) / H ** 0.5).half()
+    w_hh = (torch.randn(4 * H, H, generator=g) / H ** 0.5).half()
+    b = (torch.randn(4 * H, generator=g) * 0.3).half()
+    unit = torch.arange(H)
+    perm_ih = (torch.arange(4)[None, :] * H + unit[:, None]).reshape(-1)
+    perm_hh = (torch.arange(H // 8)[:, None, None] * 8 + torch.arange(4)[None, :, None] * H
+               + torch.arange(8)[None, None, :]).reshape(-1)
+    xt = torch.zeros(nt, t, tb, H, dtype=torch.float16)                      # tile layout
+    for i in range(nt):
+        nb = min(tb, n - i * tb)
+        xt[i, :, :nb] = x[:, i * tb:i * tb + nb]
+    xt = xt.cuda()
+    gx = torch.zeros(nt, t, cs, tb, cw, dtype=torch.float16, device="cuda")
+    native.gemm(xt, H, _dev(w_ih[perm_ih]), _dev(b[perm_ih]), gx, cw, nt * t * tb, 4 * H, H, rows_inner=tb, valid_inner=tb,
+                stride_inner=1, stride_outer=cs * tb, cb_width=cw, cb_rows=tb)
+    y = torch.full((nt, t, tb, H), float("nan"), dtype=torch.float16, device="cuda")
+    native.lstm_rec_tile(gx, _dev(w_hh[perm_hh]), y, t, n, H, reverse)
+    torch.cuda.synchronize()
+    ref = O.lstm_layer(x.float(), w_ih.float(), w_hh.float(), b.float(), torch.zeros(4 * H), reverse)
+    got = y.float().cpu().permute(1, 0, 2, 3).reshape(t, nt * tb, H)
+    assert torch.isnan(got[:, n:]).all()          # rows of chunks beyond the batch are not written
+    err = (got[:, :n] - ref).abs().max().item()
+    assert err <= 5e-3, err
+    # the two kernels agree to the rounding of h: same MMA shapes and accumulation order -> bitwise
+    gx_old = torch.empty(t, n, 4 * H, dtype=torch.float16, device="cuda")
+    native.gemm(_dev(x), H, _dev(w_ih[perm_ih]), _dev(b[perm_ih]), gx_old, 4 * H, t * n, 4 * H, H)
+    y_old = torch.empty(t, n, H, dtype=torch.float16, device="cuda")
+    native.lstm_rec(gx_old, _dev(w_hh[perm_hh]), y_old, t, n, H, reverse)
+    torch.cuda.synchronize()
+    assert torch.equal(y_old.cpu(), y.cpu().permute(1, 0, 2, 3).reshape(t, nt * tb, H)[:, :n])
+
+
 def test_tmem_conventions(native):
     """tcgen05.ld.16x256b fragment layout and the fp16-pair packing of a TMEM-resident A operand."""
     out = native.tmem_probe().numpy()

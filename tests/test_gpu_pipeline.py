@@ -26,7 +26,7 @@ def _model(name, n_lstm=5, seed=25, batchnorm=False):
 # of magnitude 4..8 is 3.9e-3 and 1e-3 is a RELATIVE bound (~1 ulp).  Against the oracle run with the same fp16
 # storage rounding points the engine must stay within a few ulp (accumulation order differs); against the pure
 # fp32 oracle the bound is what half-precision storage of 7 stacked layers costs any implementation.
-TOL_FP16_MAX, TOL_FP16_MEAN = 2.4e-2, 1.0e-3
+TOL_FP16_MAX, TOL_FP16_MEAN = 8.0e-3, 6.0e-4       # measured 3.9e-3 / 3.5e-4 (one fp16 ulp at |x| in [4, 8))
 TOL_FP32_MAX, TOL_FP32_MEAN = 6.0e-2, 3.0e-3
 
 
@@ -55,8 +55,9 @@ def test_forward_scores_match_oracle(name, n, L):
 
 
 @pytest.mark.parametrize("n", [33, 70, 128])
-def test_tile_pipelined_forward_is_bit_identical(n):
-    """Per-tile streams (the default for batches above 32 chunks) vs the single-stream layer-by-layer schedule."""
+def test_tile_pipelined_forward_is_bit_identical(n, monkeypatch):
+    """Per-tile streams (the default for batches above one tile) vs the single-stream layer-by-layer schedule, and the
+    second-generation recurrent kernel (48-chunk tiles, default) vs the first (32-chunk tiles, B200_LSTM_TILE=0)."""
     model, spec, _ = _model("hac", n_lstm=3)
     x = synth.squiggle(n, 1200, seed=n).half().cuda()
     plan = model.native_plan("cuda")
@@ -64,8 +65,12 @@ def test_tile_pipelined_forward_is_bit_identical(n):
         a = plan.forward(x, tiled=False).clone()
         b = plan.forward(x, tiled=True).clone()
         c = plan.forward(x).clone()
+        monkeypatch.setenv("B200_LSTM_TILE", "0")
+        d = plan.forward(x, tiled=False).clone()
+        e = plan.forward(x, tiled=True).clone()
     torch.cuda.synchronize()
     assert torch.equal(a, b) and torch.equal(a, c)
+    assert torch.equal(d, e) and torch.equal(a, d)
 
 
 def test_gemm_paths_agree_end_to_end():
@@ -81,6 +86,7 @@ def test_gemm_paths_agree_end_to_end():
 
 def test_identical_sequences_and_basecall_pipeline():
     """basecall() over synthetic reads == oracle forward + oracle decode + reference-style stitching."""
+    from _helpers import identity
     from bonito_b200.crf.basecall import basecall, stitch_results
     from bonito_b200.util import chunk
 
@@ -94,7 +100,9 @@ def test_identical_sequences_and_basecall_pipeline():
     lengths = [5000, 1200, 3996, 9000]  # multi-chunk, short (tiled), exactly one chunk, stubbed
     reads = [Read(f"r{i}", synth.squiggle(1, n, seed=10 + i)[0, 0].numpy()) for i, n in enumerate(lengths)]
     cs, ov = 1998, 120
-    got = {r.read_id: res for r, res in basecall(model, reads, chunksize=cs, overlap=ov, batchsize=4)}
+    got = {r.read_id: res for r, res in basecall(model, reads, chunksize=cs, overlap=ov, batchsize=4,
+                                                 qscore_calibration=True)}
+    plain = {r.read_id: res for r, res in basecall(model, reads, chunksize=cs, overlap=ov, batchsize=4)}
     for read in reads:
         chunks = chunk(torch.from_numpy(read.signal), cs, ov).half()
         with torch.no_grad():
@@ -108,10 +116,18 @@ def test_identical_sequences_and_basecall_pipeline():
         res = got[read.read_id]
         assert res["stride"] == 6 and len(res["moves"]) == len(st["moves"])
         # fp16-vs-fp32 forward differences may flip an occasional near-tie: demand >= 99% identity, report it
-        same = sum(a == b for a, b in zip(res["sequence"], want)) / max(len(want), 1)
-        print(read.read_id, len(want), len(res["sequence"]), f"identity {same:.4f}")
+        same = identity(res["sequence"], want)
+        print(read.read_id, len(want), len(res["sequence"]), f"identity (edit distance) {same:.4f}")
         assert len(res["qstring"]) == len(res["sequence"]) == int(res["moves"].sum())
-        assert abs(len(res["sequence"]) - len(want)) <= max(2, len(want) // 100)
+        assert same >= 0.99, (read.read_id, same)
+        # default = the reference's behaviour: scale 1.0 / offset 0.0, same bases, different quality string
+        assert plain[read.read_id]["sequence"] == res["sequence"]
+        moves1, seq1, qual1, _ = O.decode_native(ntc, spec["state_len"], 2.0, 1.0, 0.0)
+        st1 = stitch_results({"qstring": torch.from_numpy(qual1)}, len(read.signal), cs, ov, 6)["qstring"].numpy()
+        want_q = st1[st1 != 0].tobytes().decode()
+        if res["sequence"] == want:
+            dq = [abs(ord(a) - ord(b)) for a, b in zip(plain[read.read_id]["qstring"], want_q)]
+            assert max(dq) <= 1 and sum(d != 0 for d in dq) <= 0.02 * len(dq)
 
 
 def test_decode_of_own_scores_is_exact():
@@ -136,6 +152,48 @@ def test_decode_of_own_scores_is_exact():
         assert n0 == n1 and t1 == t0 + 1
     lens = [len(w) for w in want]
     assert min(lens) > 100 and len(set(want)) == 6
+
+
+def test_headline_shape_scores_and_sequences_match_oracle():
+    """
+    BASELINE config 2 at full size: hac, batch 512 x 9996 samples (T = 1666), 64 distinct chunks repeated 8 times.
+    16 chunks spread over the batch (different tiles, different copies) are compared with the CPU oracle run with the
+    same fp16 storage rounding: scores within fp16 tolerance (north star: 1e-3 relative; one fp16 ulp at |x| in [4, 8)
+    is 3.9e-3, the budget is two), and the base sequences of CUDA forward + CUDA decode against oracle forward + oracle
+    decode by edit distance.
+    """
+    from _helpers import edit_distance
+    from bonito_b200.decode import beam_search, to_str
+    from oracle import build_ref
+    model, spec, weights = _model("hac")
+    x64 = synth.squiggle(64, 9996, seed=7).half()
+    x = x64.repeat(8, 1, 1)
+    with torch.inference_mode():
+        scores = model(x.cuda())
+        seq, qstring, moves = beam_search(scores, scale=1.05, offset=0.2)
+    assert scores.shape == (512, 1666, 1024)
+    picks = [0, 37, 63, 64 + 5, 128 + 31, 128 + 32, 192 + 47, 256 + 48, 300, 333, 383, 400, 449, 480, 500, 511]
+    with torch.no_grad():
+        ref = O.lstm_crf_forward(weights, spec, x[picks].float(), fp16=True).permute(1, 0, 2).contiguous()
+    got = scores[picks].float().cpu()
+    err = (got - ref).abs()
+    within = (err <= 1e-3 * ref.abs().clamp(min=1.0) + 1e-3).float().mean().item()
+    print(f"headline shape vs fp16-rounding oracle: max {err.max().item():.2e} mean {err.mean().item():.2e} "
+          f"within 1e-3 rel: {within:.5f}")
+    assert err.max().item() <= 8e-3, err.max().item()
+    assert err.mean().item() <= 6e-4, err.mean().item()
+    assert within >= 0.999, within
+    o_moves, o_seq, o_q = build_ref.decode(ref.numpy(), spec["state_len"], 2.0, 1.05, 0.2)
+    total = dist = exact = 0
+    for k, i in enumerate(picks):
+        a, b = to_str(seq[i]), o_seq[k][o_seq[k] != 0].tobytes().decode()
+        d = edit_distance(a, b)
+        dist, total, exact = dist + d, total + len(b), exact + (d == 0)
+        assert len(b) > 500
+    print(f"sequences: {exact}/{len(picks)} chunks identical, edit distance {dist} over {total} bases")
+    assert dist <= 2e-3 * total, (dist, total)       # near-ties of the log-posteriors may flip under 1-ulp score changes
+    # the copies of a chunk decode identically wherever they sit in the batch
+    assert torch.equal(seq[:64], seq[448:]) and torch.equal(moves[:64], moves[64:128])
 
 
 def test_full_size_properties():
@@ -209,6 +267,7 @@ def test_score_batches_equals_compute_scores():
 def test_headline_shape_against_the_reference_fixture(golden_dir):
     """hac shape through the native engine vs scores produced by the reference's own module tree (fp32 CPU,
     tests/golden/forward_hac.npz): fp16 tolerance on the scores, same base sequences."""
+    from _helpers import identity
     from oracle.make_golden import weights_digest
     from bonito_b200.crf.model import Model
     from bonito_b200.decode import beam_search, to_str
@@ -231,5 +290,5 @@ def test_headline_shape_against_the_reference_fixture(golden_dir):
     assert err.max().item() <= 2e-2 and err.mean().item() <= 2e-3
     want = json.loads(str(gold["strings"]))
     for got, w in zip([to_str(r) for r in seq], want):
-        same = sum(a == b for a, b in zip(got, w)) / max(len(w), 1)
-        assert abs(len(got) - len(w)) <= 2 and same >= 0.98, (len(got), len(w), same)
+        same = identity(got, w)
+        assert same >= 0.99, (len(got), len(w), same)
