@@ -24,11 +24,20 @@
 //   * per (step, sub-tile) one elected thread issues 2 x 24 tcgen05.mma (M=128, N=16, K=16); eight epilogue warps pull
 //     the gate pre-activations with tcgen05.ld.16x256b (the mma-accumulator fragment: with rows ordered
 //     [8 units x (i,f,g,o)] one thread holds all four gates of a (unit, chunk)), add gx, update (c, h) in registers,
-//     stage the new h block in shared memory, push it into the h tile of all 6 CTAs with one bulk copy per peer
-//     (cp.async.bulk shared::cta -> shared::cluster, completion on the destination's tx-count mbarrier) and write Y[t].
+//     stage the new h block in shared memory and write it to Y[t].
+//   * h all-gather.  Every CTA needs the whole h_t of a sub-tile (12 KB) every step.  Pushing the blocks peer by peer
+//     through distributed shared memory (one cp.async.bulk shared::cta -> shared::cluster per peer, EXCH = 0) makes
+//     every SM send AND receive 30 KB per step over its DSMEM port: measured 3480 cycles per step for this kernel
+//     (2244 for the 8-CTA one), i.e. ~10 B/clk -- the exchange bandwidth, not the tensor core, set the step time.
+//     EXCH = 1 (default) goes through L2 instead: the block has to be written to Y[t] anyway, so the warp that wrote its
+//     16 x 16-byte pieces fences (fence.proxy.async.global) and issues ONE multicast TMA load
+//     (cp.async.bulk.tensor.2d ... .multicast::cluster, box = 8 units x 16 chunks straight out of Y) that lands the
+//     256-byte block in the h tile of all six CTAs and completes 256 bytes on each CTA's mbarrier: 24 TMA operations
+//     per CTA and step instead of 144, no DSMEM traffic at all.
 //
 // Operands: whh [4H][H] rows permuted [unit/8][gate][unit%8] (rank r owns rows 256r..256r+255);
 //           gx  [tile][T][6][48][256]  columns of rank r = [unit/8 - 8r][unit%8][gate];   y [tile][T][48][H].
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -86,6 +95,17 @@ __device__ __forceinline__ void bulk_load_global(uint32_t smem_dst, const void* 
                  "l"(gsrc), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// multicast TMA load of a 2-D box (global, through L2) into the same CTA-relative shared-memory offset of every CTA in
+// `mask`; each destination CTA's mbarrier (same CTA-relative offset) receives the box's bytes as complete_tx
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                      uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
 __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -102,18 +122,21 @@ struct Bars {
 // One epilogue warp of sub-tile `sub`: row block `blk` = 8 hidden units x 4 gates (32 TMEM lanes at lane quarter
 // blk % 4 of accumulator blk / 4), all 16 chunks of the sub-tile.
 // VARIANT (B200_LSTM_DEBUG): 0 = product; 3 = product + timeline.
-template <int VARIANT>
-__device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, int T, int nb, int reverse, uint32_t rank, int sub, int ew,
-                                              uint32_t tmem_base, uint32_t base, unsigned char* gbase, Bars bars, int lane) {
+template <int VARIANT, int EXCH>
+__device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, const CUtensorMap* map_y, int row0, int T, int nb,
+                                              int reverse, uint32_t rank, int sub, int ew, uint32_t tmem_base,
+                                              uint32_t base, unsigned char* gbase, Bars bars, int lane) {
     const int r = lane >> 2, q = lane & 3;
     const int quarter = ew & 3, which = ew >> 2, blk = which * 4 + quarter;
     const int u0 = (int)rank * UPC + blk * 8;                                   // first unit of this block
     // destination inside a peer's h tile: k-chunk (u0 / 8): 256 contiguous bytes
     const uint32_t dst_off = (uint32_t)(u0 >> 3) * (SN * 16);
     // shared::cluster window of peer d relative to this CTA's (mapa is affine in the offset); own rank last
-    uint32_t peer_shift[CS];
+    uint32_t peer_shift[EXCH == 0 ? CS : 1];
+    if (EXCH == 0) {
 #pragma unroll
-    for (int d = 0; d < CS; ++d) peer_shift[d] = mapa(base, (rank + 1u + (uint32_t)d) % CS) - base;
+        for (int d = 0; d < CS; ++d) peer_shift[d] = mapa(base, (rank + 1u + (uint32_t)d) % CS) - base;
+    }
     float c_state[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     // this lane's gx values inside a ring slot: chunk 8j + 2q + e, columns blk*32 + r*4 .. +3 (gates i,f,g,o of unit r)
     const uint32_t gx_lane = base + OFF_GX + (uint32_t)(sub * GXD) * GXS + (uint32_t)(2 * q) * (ROWS * 2) + (uint32_t)(blk * 32 + r * 4) * 2;
@@ -162,18 +185,34 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, int T, int
                 c_state[j][e] = c;
                 stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(so * tanh_f(c));
             }
-        fence_proxy_async_smem();   // staged block (generic stores) -> visible to the bulk-copy engine
-        __syncwarp();
-        if (tl && ew == 0) g_timeline6[ts][4] = clock64();
-        if (step + 1 < T && elect_one_sync()) {   // one lane: six back-to-back bulk copies, one per peer
-            const uint32_t dst = base + OFF_H + (uint32_t)(sub * 2 + (p ^ 1)) * HT + dst_off, src = base + stage_off;
-            const uint32_t bar = bars.hfull(sub, p ^ 1);
+        if (EXCH == 0) {
+            fence_proxy_async_smem();   // staged block (generic stores) -> visible to the bulk-copy engine
+            __syncwarp();
+            if (tl && ew == 0) g_timeline6[ts][4] = clock64();
+            if (step + 1 < T && elect_one_sync()) {   // one lane: six back-to-back bulk copies, one per peer
+                const uint32_t dst = base + OFF_H + (uint32_t)(sub * 2 + (p ^ 1)) * HT + dst_off, src = base + stage_off;
+                const uint32_t bar = bars.hfull(sub, p ^ 1);
 #pragma unroll
-            for (int d = 0; d < CS; ++d) bulk_copy_to_peer(dst + peer_shift[d], src, STAGE_WARP, bar + peer_shift[d]);
-        }
-        if (y_ok) {   // chunk `lane` of the sub-tile: its 8 units
-            const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];
-            *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;
+                for (int d = 0; d < CS; ++d) bulk_copy_to_peer(dst + peer_shift[d], src, STAGE_WARP, bar + peer_shift[d]);
+            }
+            if (y_ok) {   // chunk `lane` of the sub-tile: its 8 units
+                const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];
+                *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;
+            }
+        } else {
+            __syncwarp();
+            if (tl && ew == 0) g_timeline6[ts][4] = clock64();
+            if (y_ok) {   // chunk `lane` of the sub-tile: its 8 units -> Y[t]
+                const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];
+                *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;
+            }
+            if (step + 1 < T) {
+                fence_proxy_async_global();   // the pieces just written (generic proxy) -> visible to the TMA (async proxy)
+                __syncwarp();
+                if (elect_one_sync())        // box {8 units, 16 chunks} of Y[t] -> this k-chunk of every CTA's h tile
+                    tma_load_2d_multicast(base + OFF_H + (uint32_t)(sub * 2 + (p ^ 1)) * HT + dst_off, map_y,
+                                          bars.hfull(sub, p ^ 1), u0, row0 + t * NB + sub * SN, (uint16_t)((1u << CS) - 1u));
+            }
         }
         if (tl) g_timeline6[ts][ew == 0 ? 5 : 7] = clock64();
         __syncwarp();
@@ -187,10 +226,10 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, int T, int
 // complete, which needs this CTA's own epilogue warps of (u, s-1) to have sent, i.e. to have consumed gx (u, s-1).
 // TMEM accumulator reuse: the MMAs of (u, s+1) are issued after the h tile (u, s+1) is complete, i.e. after every
 // epilogue warp of (u, s) has drained its accumulator block (tcgen05.wait::ld precedes the send).
-template <int VARIANT>
+template <int VARIANT, int EXCH>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(THREADS, 1)
-lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh, __half* __restrict__ y, int T, int N,
-                    int reverse) {
+lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh, __half* __restrict__ y,
+                    const __grid_constant__ CUtensorMap map_y, int T, int N, int reverse) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -205,8 +244,10 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
     const int nsub = (nb + SN - 1) / SN;            // active sub-tiles (the same in every CTA of the cluster)
     gx += (size_t)tile * T * (CS * NB * ROWS);
     y += (size_t)tile * T * (NB * H);
+    const int row0 = tile * T * NB;                 // first row of this tile in the [tiles*T*48][H] view of Y (map_y)
 
     if (tid == 0) {
+        if (EXCH == 1) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_y));
         for (uint32_t i = 0; i < N_BARS; ++i) mbar_init(bars.base + 8 * i, 1);
         mbar_fence_init();
         // every fill of an h tile is SN*H*2 bytes of bulk-copy traffic from the 6 CTAs of the cluster
@@ -305,7 +346,8 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
         }
     } else {
         const int sub = warp / EW, ew = warp % EW;
-        if (sub < nsub) epilogue_warp<VARIANT>(y, T, nb, reverse, rank, sub, ew, tmem_base, base, gbase, bars, lane);
+        if (sub < nsub)
+            epilogue_warp<VARIANT, EXCH>(y, &map_y, row0, T, nb, reverse, rank, sub, ew, tmem_base, base, gbase, bars, lane);
     }
 
     tc_fence_before();
@@ -319,20 +361,58 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
 int lstm_rec_tile_chunks(int hidden) { return hidden == H ? NB : 0; }
 int lstm_rec_tile_cluster(int hidden) { return hidden == H ? CS : 0; }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
 // gx [tiles][T][6][48][256], y [tiles][T][48][H]; tiles = ceil(N / 48), the last one may be partial
 int launch_lstm_rec_tc6(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
                         cudaStream_t stream) {
     B200_REQUIRE(hidden == H, "lstm_rec_tile: hidden size %d is not supported (384)", hidden);
+    B200_REQUIRE(((uintptr_t)gx % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)whh % 16) == 0,
+                 "lstm_rec_tile: operands must be 16-byte aligned");
     const int tiles = (N + NB - 1) / NB;
     const char* dbg = getenv("B200_LSTM_DEBUG");
     const int variant = dbg ? atoi(dbg) : 0;
-    if (variant == 3) {
-        B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc6_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        lstm_rec_tc6_kernel<3><<<tiles * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, T, N, reverse);
-    } else {
-        B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc6_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        lstm_rec_tc6_kernel<0><<<tiles * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, T, N, reverse);
+    const char* ex = getenv("B200_LSTM_EXCH");          // "dsmem": peer-to-peer bulk copies; default: multicast TMA through Y
+    const bool dsmem = ex && ex[0] == 'd';
+    // Y as a 2-D tensor [tiles*T*48 rows][H]; box = 8 units x 16 chunks = one k-chunk block of an h tile (no swizzle)
+    CUtensorMap map_y;
+    {
+        EncodeTiledFn fn = encode_fn();
+        B200_REQUIRE(fn != nullptr, "lstm_rec_tile: cuTensorMapEncodeTiled is not available from the driver");
+        cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)tiles * (cuuint64_t)T * NB};
+        cuuint64_t strides[1] = {(cuuint64_t)H * 2};
+        cuuint32_t box[2] = {8, (cuuint32_t)SN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = fn(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)y, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        B200_REQUIRE(r == CUDA_SUCCESS, "lstm_rec_tile: cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
+#define LAUNCH6(v, e)                                                                                                   \
+    do {                                                                                                                \
+        B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc6_kernel<v, e>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                             (int)SMEM_BYTES));                                                         \
+        lstm_rec_tc6_kernel<v, e><<<tiles * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, map_y, T, N, reverse);       \
+    } while (0)
+    if (variant == 3 && dsmem) LAUNCH6(3, 0);
+    else if (variant == 3) LAUNCH6(3, 1);
+    else if (dsmem) LAUNCH6(0, 0);
+    else LAUNCH6(0, 1);
+#undef LAUNCH6
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -12,6 +12,9 @@ Contents
                    replaced by flash-attn's torch reference functions, see oracle/reference_shim.load_transformer)
   forward_hac.npz  the headline shape (H = 384, 5 LSTM, k = 4) through the reference module tree, fp32 CPU: input, scores
                    without the blank column [N,T,1024], decode_batch strings, digest of the seeded weights
+  revcomp.npz      CTC_CRF.reverse_complement of the reference on small random scores, k = 3, 4, 5
+  forward_sup_wide.npz  the sup v5 width (d_model 512, 8 heads, ff 2048, k = 5), 6 layers, through the reference's
+                   bonito.transformer classes: input, conv output, layers 0 and 5, scores [N,2T',4096]; weights by digest
   forward_fast.npz reference module tree (bonito.nn via from_dict, BatchNorm folded by fuse_bn_) forward in
                    fp32 on CPU: input, every parameter, per-layer features, scores [T,N,C+blanks];
                    + decode_batch strings (reference glue over the oracle's posteriors stand-in)
@@ -179,18 +182,65 @@ def forward_hac(ref):
     print("forward_hac.npz scores", tuple(ntc.shape), "strings", [len(s) for s in strings], "max|s|", float(ntc.abs().max()))
 
 
+def revcomp(ref):
+    """CTC_CRF.reverse_complement (bonito/crf/model.py:84-96) of the reference on small random blank-expanded scores."""
+    out = {}
+    gen = torch.Generator().manual_seed(3)
+    for k, (T, N) in ((3, (7, 2)), (4, (5, 3)), (5, (3, 1))):
+        sd = ref.crf_model.CTC_CRF(k, ["N", "A", "C", "G", "T"])
+        scores = torch.randn(T, N, sd.n_score(), generator=gen)
+        out[f"in_k{k}"] = scores.numpy()
+        out[f"out_k{k}"] = sd.reverse_complement(scores).numpy()
+    np.savez_compressed(os.path.join(OUT, "revcomp.npz"), **out)
+    print("revcomp.npz", {k: v.shape for k, v in out.items()})
+
+
+def forward_sup_wide(ref):
+    """The sup v5 width (d_model 512, 8 heads of 64, feed-forward 2048, the full 5-convolution stack, k = 5: 4096 scores per
+    frame), 6 layers, through the reference's own transformer classes in fp32 on the CPU.  The 24 M seeded weights are
+    regenerated by the tests (`synth.make_sup_weights(spec, seed=11)`, plain torch.randn draws) and checked by digest."""
+    tm = reference_shim.load_transformer()
+    spec = synth.sup_spec(depth=6)
+    cfg = synth.sup_config(spec)
+    torch.manual_seed(25)
+    model = tm.Model(cfg)
+    weights = synth.make_sup_weights(spec, seed=11)
+    missing, unexpected = model.load_state_dict(synth.sup_state_dict(spec, weights), strict=False)
+    assert not unexpected and all("rotary" in k or "inv_freq" in k for k in missing), (missing, unexpected)
+    model.eval()
+    x = synth.squiggle(2, 600, seed=16).half().float()      # fp16-representable input
+    with torch.inference_mode():
+        scores = model(x)                                   # [2T', N, C + blanks]
+        conv = model.encoder.conv(x)                        # [N, T', d]
+        h, layers = conv, []
+        for layer in model.encoder.transformer_encoder:
+            h = layer(h)
+            layers.append(h)
+    t, n, _ = scores.shape
+    s5 = scores.reshape(t, n, -1, 5)
+    assert torch.all(s5[..., 0] == 2.0)
+    ntc = s5[..., 1:].reshape(t, n, -1).permute(1, 0, 2).contiguous()
+    out = {"x": x.numpy().astype(np.float16), "scores_ntc": ntc.numpy(), "conv": conv.numpy(),
+           "layer0": layers[0].numpy(), "layer5": layers[5].numpy(), "digest": np.array(weights_digest(weights)),
+           "seed": np.array(11), "depth": np.array(6), "stride": np.array(model.stride)}
+    np.savez_compressed(os.path.join(OUT, "forward_sup_wide.npz"), **out)
+    print("forward_sup_wide.npz scores", tuple(ntc.shape), "std %.2f max %.1f" % (float(ntc.std()), float(ntc.abs().max())))
+
+
 def get_stride_ok(ref, model):
     return ref.crf_model.get_stride(model.encoder) == 6 and model.stride == 6
 
 
-def main():
+def main(names=None):
+    """`python -m oracle.make_golden [name ...]`: all fixtures, or only the named ones."""
     os.makedirs(OUT, exist_ok=True)
     ref = reference_shim.load()
-    host_logic(ref)
-    forward_fast(ref)
-    forward_sup(ref)
-    forward_hac(ref)
+    makers = dict(host_logic=host_logic, forward_fast=forward_fast, forward_sup=forward_sup, forward_hac=forward_hac,
+                  revcomp=revcomp, forward_sup_wide=forward_sup_wide)
+    for name in (names or list(makers)):
+        makers[name](ref)
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(sys.argv[1:])

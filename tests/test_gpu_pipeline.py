@@ -183,15 +183,23 @@ def test_headline_shape_scores_and_sequences_match_oracle():
     assert err.max().item() <= 8e-3, err.max().item()
     assert err.mean().item() <= 6e-4, err.mean().item()
     assert within >= 0.999, within
+    # (1) the decoder at full length on real scores: the oracle decoder fed the CUDA scores gives the CUDA sequences exactly
+    c_moves, c_seq, c_q = build_ref.decode(got.numpy(), spec["state_len"], 2.0, 1.05, 0.2)
+    for k, i in enumerate(picks):
+        assert to_str(seq[i]) == c_seq[k][c_seq[k] != 0].tobytes().decode(), i
+    # (2) end to end: oracle forward + oracle decode against CUDA forward + CUDA decode.  The two forwards differ by at most
+    # one fp16 ulp in 0.003 % of the scores; where the posterior is flat (synthetic random weights have such stretches) that
+    # is enough to move a few calls, so identity is asserted by edit distance and the exact-match count is reported.
     o_moves, o_seq, o_q = build_ref.decode(ref.numpy(), spec["state_len"], 2.0, 1.05, 0.2)
     total = dist = exact = 0
     for k, i in enumerate(picks):
         a, b = to_str(seq[i]), o_seq[k][o_seq[k] != 0].tobytes().decode()
         d = edit_distance(a, b)
         dist, total, exact = dist + d, total + len(b), exact + (d == 0)
-        assert len(b) > 500
-    print(f"sequences: {exact}/{len(picks)} chunks identical, edit distance {dist} over {total} bases")
-    assert dist <= 2e-3 * total, (dist, total)       # near-ties of the log-posteriors may flip under 1-ulp score changes
+        assert len(b) > 500 and d <= 0.03 * len(b), (i, d, len(b))
+    print(f"sequences: {exact}/{len(picks)} chunks identical, edit distance {dist} over {total} bases "
+          f"(identity {1 - dist / total:.5f})")
+    assert dist <= 1e-2 * total and exact >= len(picks) // 2, (dist, total, exact)
     # the copies of a chunk decode identically wherever they sit in the batch
     assert torch.equal(seq[:64], seq[448:]) and torch.equal(moves[:64], moves[64:128])
 
@@ -292,3 +300,33 @@ def test_headline_shape_against_the_reference_fixture(golden_dir):
     for got, w in zip([to_str(r) for r in seq], want):
         same = identity(got, w)
         assert same >= 0.99, (len(got), len(w), same)
+
+
+def test_reverse_complement_on_the_native_layout():
+    """--revcomp (bonito/crf/basecall.py:35, bonito/crf/model.py:84-96): the native-layout helper equals the reference
+    definition on the blank-expanded [T, N, C] layout (pinned on the CPU against tests/golden/revcomp.npz), and basecalling
+    the reverse-complemented scores yields the reverse complement of the sequence."""
+    from _helpers import identity
+    from bonito_b200.crf.basecall import _revcomp_native, compute_scores
+    from bonito_b200.decode import to_str
+    model, spec, _ = _model("hac", n_lstm=2)
+    g = torch.Generator().manual_seed(12)
+    scores = (torch.randn(3, 50, 1024, generator=g) * 1.7).clamp(-5, 5).half()
+    got = _revcomp_native(model, scores.cuda(), 2.0).cpu()
+    full = torch.nn.functional.pad(scores.permute(1, 0, 2).reshape(50, 3, 256, 4), (1, 0), value=2.0).reshape(50, 3, -1)
+    want = model.seqdist.reverse_complement(full).reshape(50, 3, 256, 5)[..., 1:].reshape(50, 3, 1024).permute(1, 0, 2)
+    assert torch.equal(got, want)
+    assert torch.equal(_revcomp_native(model, got.cuda(), 2.0).cpu(), scores)
+
+    x = synth.squiggle(5, 3996, seed=31)
+    fwd = compute_scores(model, x)
+    rev = compute_scores(model, x, reverse=True)
+    comp = str.maketrans("ACGT", "TGCA")
+    exact = 0
+    for a, b in zip(fwd["sequence"], rev["sequence"]):
+        sa, sb = to_str(a), to_str(b)
+        assert len(sa) > 200
+        same = identity(sa[::-1].translate(comp), sb)
+        exact += same == 1.0
+        assert same >= 0.99, same
+    print("reverse-complement basecalls identical to the reverse complement of the forward basecall:", exact, "of 5")

@@ -152,3 +152,29 @@ def test_phred_and_mean_qscore():
     assert util.phred(0.9) == chr(10 + 33) and util.phred(1.0) == chr(40 + 33)
     assert util.phred(0.99, scale=1.05, bias=0.2) == chr(int(np.round(20 * 1.05 + 0.2)) + 33)
     assert abs(util.mean_qscore_from_qstring("5" * 10) - 20.0) < 1e-9
+
+
+def test_reverse_complement_matches_reference(golden_dir):
+    """CTC_CRF.reverse_complement against the reference's own function (tests/golden/revcomp.npz), k = 3, 4, 5; and the
+    definition's involution property."""
+    from bonito_b200.crf.model import CTC_CRF
+    gold = np.load(os.path.join(golden_dir, "revcomp.npz"))
+    for k in (3, 4, 5):
+        sd = CTC_CRF(k, ["N", "A", "C", "G", "T"])
+        x = torch.from_numpy(gold[f"in_k{k}"])
+        got = sd.reverse_complement(x)
+        assert torch.equal(got, torch.from_numpy(gold[f"out_k{k}"]))
+        assert torch.equal(sd.reverse_complement(got), x)
+
+
+def test_fmt_rna_flips_sequence_and_qstring():
+    """fmt(..., rna=True) reverses sequence and qstring (bonito/crf/basecall.py:48-55); moves stay as they are."""
+    from bonito_b200.crf.basecall import fmt
+    seq = torch.tensor([0, 65, 0, 67, 71, 0, 84], dtype=torch.uint8)
+    qs = torch.tensor([0, 40, 0, 41, 42, 0, 43], dtype=torch.uint8)
+    mv = torch.tensor([0, 1, 0, 1, 1, 0, 1], dtype=torch.uint8)
+    attrs = {"sequence": seq, "qstring": qs, "moves": mv}
+    dna, rna = fmt(6, attrs), fmt(6, attrs, rna=True)
+    assert dna["sequence"] == "ACGT" and dna["qstring"] == "()*+"
+    assert rna["sequence"] == "TGCA" and rna["qstring"] == "+*)(" and rna["stride"] == 6
+    assert np.array_equal(rna["moves"], mv.numpy())

@@ -69,3 +69,29 @@ def test_use_koi_rewrites_the_encoder_like_the_reference():
     assert crf.expand_blanks is False
     with pytest.raises(Exception):      # armed native path without a CUDA device: loud failure
         model(torch.zeros(1, 1, 1200))
+
+
+def _wide(golden_dir):
+    from oracle.make_golden import weights_digest
+    gold = np.load(os.path.join(golden_dir, "forward_sup_wide.npz"))
+    spec = synth.sup_spec(depth=int(gold["depth"]))
+    weights = synth.make_sup_weights(spec, seed=int(gold["seed"]))
+    if weights_digest(weights) != str(gold["digest"]):
+        pytest.skip("seeded sup weights differ on this machine: fixture not comparable")
+    return gold, spec, weights
+
+
+def test_oracle_matches_reference_transformer_at_sup_width(golden_dir):
+    """d_model 512, 8 heads, ff 2048, 6 layers, k = 5: the oracle against the reference's own classes (fp32)."""
+    gold, spec, w = _wide(golden_dir)
+    with torch.no_grad():
+        s, feats = TO.transformer_forward(w, spec, torch.from_numpy(gold["x"].astype(np.float32)), return_features=True)
+    np.testing.assert_allclose(feats["conv4"].permute(0, 2, 1).numpy(), gold["conv"], atol=5e-5)
+    np.testing.assert_allclose(feats["layer0"].numpy(), gold["layer0"], atol=5e-5)
+    np.testing.assert_allclose(feats["layer5"].numpy(), gold["layer5"], atol=1e-4)
+    np.testing.assert_allclose(s.numpy(), gold["scores_ntc"], atol=5e-4)       # scores reach |x| ~ 11 (x5 scale)
+    # the same-rounding (fp16 storage) oracle the GPU tests compare with stays within half-precision distance of it
+    with torch.no_grad():
+        s16 = TO.transformer_forward(w, spec, torch.from_numpy(gold["x"].astype(np.float32)), fp16=True)
+    err = (s16 - torch.from_numpy(gold["scores_ntc"])).abs()
+    assert err.max().item() <= 8e-2 and err.mean().item() <= 6e-3, (err.max().item(), err.mean().item())
