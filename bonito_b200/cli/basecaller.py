@@ -2,7 +2,8 @@
 `bonito_b200 basecaller <model_directory> <reads_directory>` -- the flag surface of the reference's
 `bonito basecaller` (`/root/reference/bonito/cli/basecaller.py:168-199`) over the B200 engine.
 Alignment (`--reference`, needs mappy) and CTC training-data export (`--save-ctc`) are outside the hot path and
-exit with an explanation; output is unaligned FASTQ on stdout.
+exit with an explanation; output is unaligned FASTQ, or unaligned SAM text with the `mv:B:c` move table when stdout is
+redirected to a `.sam` file (the reference's `biofmt` rule, bonito/io.py:35-54).
 """
 
 import sys
@@ -13,7 +14,7 @@ from time import perf_counter
 
 import numpy as np
 
-from bonito_b200.io import Writer
+from bonito_b200.io import Writer, biofmt
 from bonito_b200.nn import fuse_bn_
 from bonito_b200.reader import Reader
 from bonito_b200.util import init, load_model, load_symbol
@@ -37,7 +38,11 @@ def main(args):
     except FileNotFoundError:
         sys.stderr.write("> error: no suitable files found in %s\n" % args.reads_directory)
         exit(1)
-    sys.stderr.write("> outputting unaligned fastq\n")
+    fmt = biofmt(aligned=False)
+    if fmt.mode not in ("wfq", "w"):
+        sys.stderr.write(f"> error: {fmt.name} output needs htslib, which this build does not bundle; redirect to .sam or .fastq\n")
+        exit(1)
+    sys.stderr.write(f"> outputting {fmt.aligned} {fmt.name}\n")
     sys.stderr.write(f"> loading model {args.model_directory}\n")
     try:
         model = load_model(args.model_directory, args.device, weights=args.weights if args.weights > 0 else None,
@@ -63,7 +68,9 @@ def main(args):
     params = model.config["basecaller"]
     results = basecall(model, reads, reverse=args.revcomp, rna=args.rna, batchsize=params["batchsize"],
                        chunksize=params["chunksize"], overlap=params["overlap"])
-    writer = Writer(results, min_qscore=args.min_qscore)
+    import os
+    writer = Writer(results, min_qscore=args.min_qscore, mode=fmt.mode,
+                    group_key=os.path.basename(os.path.normpath(args.model_directory)))
     t0 = perf_counter()
     writer.start()
     writer.join()

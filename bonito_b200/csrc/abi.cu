@@ -25,12 +25,15 @@ int launch_lstm_rec_tc(const __half* gx, const __half* whh, __half* y, int T, in
 int launch_tmem_probe(float* out, cudaStream_t stream);
 int lstm_rec_tile_chunks(int hidden);
 int lstm_rec_tile_cluster(int hidden);
-int launch_lstm_rec_tc6(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
-                        cudaStream_t stream);
+int launch_lstm_rec_tc6(const __half* gx, const __half* whh, __half* y, void* workspace, int T, int N, int hidden,
+                        int reverse, cudaStream_t stream);
+size_t lstm_rec_tile_workspace_bytes(int N);
 int copy_lstm_timeline6(long long* host_out, int max_steps);
 int copy_lstm_timeline(long long* host_out, int max_steps);
 int lstm_rec_tc_max_clusters();
 int debug_max_clusters(int cluster_size, int threads, int smem_bytes);
+int launch_exchange_bench(int mode, int steps, int delay, int clusters, unsigned char* staging, long long* out,
+                          cudaStream_t stream);
 int launch_mma_bench(int ts_mode, int n, int iters, int chains, int blocks, long long* out, cudaStream_t stream);
 size_t crf_decode_workspace_bytes(int N, int T, int state_len);
 int launch_crf_decode(const __half* scores, int N, int T, int state_len, float blank, float qscale, float qbias,
@@ -160,12 +163,14 @@ int b200_lstm_tile_chunks(int hidden) { return lstm_rec_tile_chunks(hidden); }
 
 int b200_lstm_tile_cluster(int hidden) { return lstm_rec_tile_cluster(hidden); }
 
-int b200_lstm_rec_tile_fwd(const void* gx, const void* whh, void* y, int t, int n, int hidden, int reverse,
-                           void* stream) {
-    B200_REQUIRE(gx && whh && y, "lstm_rec_tile: null pointer argument");
+size_t b200_lstm_rec_tile_workspace_bytes(int n) { return lstm_rec_tile_workspace_bytes(n); }
+
+int b200_lstm_rec_tile_fwd(const void* gx, const void* whh, void* y, void* workspace, int t, int n, int hidden,
+                           int reverse, void* stream) {
+    B200_REQUIRE(gx && whh && y && workspace, "lstm_rec_tile: null pointer argument");
     B200_REQUIRE(t >= 0 && n >= 0, "lstm_rec_tile: bad sizes t=%d n=%d", t, n);
     if (t == 0 || n == 0) return 0;
-    return launch_lstm_rec_tc6((const __half*)gx, (const __half*)whh, (__half*)y, t, n, hidden, reverse,
+    return launch_lstm_rec_tc6((const __half*)gx, (const __half*)whh, (__half*)y, workspace, t, n, hidden, reverse,
                                (cudaStream_t)stream);
 }
 
@@ -180,6 +185,12 @@ int b200_debug_tmem_probe(void* out, void* stream) {
 }
 
 int b200_debug_lstm_max_clusters(void) { return lstm_rec_tc_max_clusters(); }
+
+int b200_debug_exchange_bench(int mode, int steps, int delay, int clusters, void* staging, void* out, void* stream) {
+    B200_REQUIRE(staging && out && steps > 0 && clusters > 0 && clusters <= 22 && (mode == 0 || (mode >= 2 && mode <= 4)),
+                 "exchange_bench: bad arguments");
+    return launch_exchange_bench(mode, steps, delay, clusters, (unsigned char*)staging, (long long*)out, (cudaStream_t)stream);
+}
 
 int b200_debug_max_clusters(int cluster_size, int threads, int smem_bytes) {
     return debug_max_clusters(cluster_size, threads, smem_bytes);

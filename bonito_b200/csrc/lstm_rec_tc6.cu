@@ -27,17 +27,18 @@
 //     stage the new h block in shared memory and write it to Y[t].
 //   * h all-gather.  Every CTA needs the whole h_t of a sub-tile (12 KB) every step.  Pushing the blocks peer by peer
 //     through distributed shared memory (one cp.async.bulk shared::cta -> shared::cluster per peer, EXCH = 0) makes
-//     every SM send AND receive 30 KB per step over its DSMEM port: measured 3480 cycles per step for this kernel
-//     (2244 for the 8-CTA one), i.e. ~10 B/clk -- the exchange bandwidth, not the tensor core, set the step time.
-//     EXCH = 1 (default) goes through L2 instead: the block has to be written to Y[t] anyway, so the warp that wrote its
-//     16 x 16-byte pieces fences (fence.proxy.async.global) and issues ONE multicast TMA load
-//     (cp.async.bulk.tensor.2d ... .multicast::cluster, box = 8 units x 16 chunks straight out of Y) that lands the
-//     256-byte block in the h tile of all six CTAs and completes 256 bytes on each CTA's mbarrier: 24 TMA operations
-//     per CTA and step instead of 144, no DSMEM traffic at all.
+//     every SM send AND receive 30 KB per step over its DSMEM port: 3480 cycles per step measured for this kernel with
+//     it (2244 for the 8-CTA one: both ~18 B/clk per SM, in + out) -- the exchange bandwidth, not the tensor core, set
+//     the step time.  EXCH = 1 (default) goes through L2: the warp writes its 256-byte block to a staging buffer in
+//     global memory (which stays in L2), fences (fence.proxy.async.global) and issues ONE multicast bulk copy
+//     (cp.async.bulk ... global -> shared::cluster, .multicast::cluster) that lands the block in the h tile of all six CTAs
+//     and completes 256 bytes on each CTA's mbarrier: 24 TMA operations per CTA and step instead of 144 and no DSMEM
+//     traffic.  Exchange skeleton alone (scripts/exchange_bench.py): 840 vs 1830 cycles per step.  (A multicast TENSOR
+//     load straight out of Y, box = 8 units x 16 chunks, needs no staging buffer but measured 10700 cycles per step: its
+//     16-byte box rows are one L2 request each.)
 //
 // Operands: whh [4H][H] rows permuted [unit/8][gate][unit%8] (rank r owns rows 256r..256r+255);
 //           gx  [tile][T][6][48][256]  columns of rank r = [unit/8 - 8r][unit%8][gate];   y [tile][T][48][H].
-#include <cuda.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -95,14 +96,12 @@ __device__ __forceinline__ void bulk_load_global(uint32_t smem_dst, const void* 
                  "l"(gsrc), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// multicast TMA load of a 2-D box (global, through L2) into the same CTA-relative shared-memory offset of every CTA in
-// `mask`; each destination CTA's mbarrier (same CTA-relative offset) receives the box's bytes as complete_tx
-__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                                      uint16_t mask) {
+// multicast bulk copy global (L2) -> the same CTA-relative shared-memory offset of every CTA in `mask`; each destination
+// CTA's mbarrier (same CTA-relative offset) receives `bytes` of complete_tx
+__device__ __forceinline__ void bulk_multicast(uint32_t dst, const void* gsrc, uint32_t bytes, uint32_t bar, uint16_t mask) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::
+            "r"(dst), "l"(gsrc), "r"(bytes), "r"(bar), "h"(mask)
         : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
@@ -123,7 +122,7 @@ struct Bars {
 // blk % 4 of accumulator blk / 4), all 16 chunks of the sub-tile.
 // VARIANT (B200_LSTM_DEBUG): 0 = product; 3 = product + timeline.
 template <int VARIANT, int EXCH>
-__device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, const CUtensorMap* map_y, int row0, int T, int nb,
+__device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned char* __restrict__ hx, int T, int nb,
                                               int reverse, uint32_t rank, int sub, int ew, uint32_t tmem_base,
                                               uint32_t base, unsigned char* gbase, Bars bars, int lane) {
     const int r = lane >> 2, q = lane & 3;
@@ -202,16 +201,19 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, const CUte
         } else {
             __syncwarp();
             if (tl && ew == 0) g_timeline6[ts][4] = clock64();
-            if (y_ok) {   // chunk `lane` of the sub-tile: its 8 units -> Y[t]
+            // staging block of this warp for the tile (sub, parity p^1): [k-chunk u0/8][16 chunks][16 B], the h-tile layout
+            unsigned char* g = hx + (size_t)((p ^ 1) * NS + sub) * HT + dst_off;
+            if (lane < SN) {   // chunk `lane` of the sub-tile: its 8 units -> Y[t] and -> the staging block
                 const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];
-                *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;
+                if (y_ok) *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;
+                if (step + 1 < T) reinterpret_cast<uint4*>(g)[lane] = chunk;
             }
             if (step + 1 < T) {
-                fence_proxy_async_global();   // the pieces just written (generic proxy) -> visible to the TMA (async proxy)
+                fence_proxy_async_global();   // the block just written (generic proxy) -> visible to the TMA (async proxy)
                 __syncwarp();
-                if (elect_one_sync())        // box {8 units, 16 chunks} of Y[t] -> this k-chunk of every CTA's h tile
-                    tma_load_2d_multicast(base + OFF_H + (uint32_t)(sub * 2 + (p ^ 1)) * HT + dst_off, map_y,
-                                          bars.hfull(sub, p ^ 1), u0, row0 + t * NB + sub * SN, (uint16_t)((1u << CS) - 1u));
+                if (elect_one_sync())
+                    bulk_multicast(base + OFF_H + (uint32_t)(sub * 2 + (p ^ 1)) * HT + dst_off, g, STAGE_WARP,
+                                   bars.hfull(sub, p ^ 1), (uint16_t)((1u << CS) - 1u));
             }
         }
         if (tl) g_timeline6[ts][ew == 0 ? 5 : 7] = clock64();
@@ -229,7 +231,7 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, const CUte
 template <int VARIANT, int EXCH>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(THREADS, 1)
 lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh, __half* __restrict__ y,
-                    const __grid_constant__ CUtensorMap map_y, int T, int N, int reverse) {
+                    unsigned char* __restrict__ hx, int T, int N, int reverse) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -244,10 +246,9 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
     const int nsub = (nb + SN - 1) / SN;            // active sub-tiles (the same in every CTA of the cluster)
     gx += (size_t)tile * T * (CS * NB * ROWS);
     y += (size_t)tile * T * (NB * H);
-    const int row0 = tile * T * NB;                 // first row of this tile in the [tiles*T*48][H] view of Y (map_y)
+    hx += (size_t)tile * (2 * NS * HT);            // this tile's exchange staging: [parity][sub][h tile]
 
     if (tid == 0) {
-        if (EXCH == 1) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_y));
         for (uint32_t i = 0; i < N_BARS; ++i) mbar_init(bars.base + 8 * i, 1);
         mbar_fence_init();
         // every fill of an h tile is SN*H*2 bytes of bulk-copy traffic from the 6 CTAs of the cluster
@@ -347,7 +348,7 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
     } else {
         const int sub = warp / EW, ew = warp % EW;
         if (sub < nsub)
-            epilogue_warp<VARIANT, EXCH>(y, &map_y, row0, T, nb, reverse, rank, sub, ew, tmem_base, base, gbase, bars, lane);
+            epilogue_warp<VARIANT, EXCH>(y, hx, T, nb, reverse, rank, sub, ew, tmem_base, base, gbase, bars, lane);
     }
 
     tc_fence_before();
@@ -361,52 +362,28 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
 int lstm_rec_tile_chunks(int hidden) { return hidden == H ? NB : 0; }
 int lstm_rec_tile_cluster(int hidden) { return hidden == H ? CS : 0; }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+size_t lstm_rec_tile_workspace_bytes(int N) { return (size_t)((N + NB - 1) / NB) * (2 * NS * HT); }
 
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// gx [tiles][T][6][48][256], y [tiles][T][48][H]; tiles = ceil(N / 48), the last one may be partial
-int launch_lstm_rec_tc6(const __half* gx, const __half* whh, __half* y, int T, int N, int hidden, int reverse,
-                        cudaStream_t stream) {
+// gx [tiles][T][6][48][256], y [tiles][T][48][H]; tiles = ceil(N / 48), the last one may be partial;
+// workspace: lstm_rec_tile_workspace_bytes(N) bytes of exchange staging (contents irrelevant)
+int launch_lstm_rec_tc6(const __half* gx, const __half* whh, __half* y, void* workspace, int T, int N, int hidden,
+                        int reverse, cudaStream_t stream) {
     B200_REQUIRE(hidden == H, "lstm_rec_tile: hidden size %d is not supported (384)", hidden);
-    B200_REQUIRE(((uintptr_t)gx % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)whh % 16) == 0,
+    B200_REQUIRE(((uintptr_t)gx % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)whh % 16) == 0 &&
+                     ((uintptr_t)workspace % 16) == 0,
                  "lstm_rec_tile: operands must be 16-byte aligned");
     const int tiles = (N + NB - 1) / NB;
     const char* dbg = getenv("B200_LSTM_DEBUG");
     const int variant = dbg ? atoi(dbg) : 0;
-    const char* ex = getenv("B200_LSTM_EXCH");          // "dsmem": peer-to-peer bulk copies; default: multicast TMA through Y
+    // default: multicast bulk copies out of the L2 staging buffer; "dsmem": peer-to-peer bulk copies (cross-check)
+    const char* ex = getenv("B200_LSTM_EXCH");
     const bool dsmem = ex && ex[0] == 'd';
-    // Y as a 2-D tensor [tiles*T*48 rows][H]; box = 8 units x 16 chunks = one k-chunk block of an h tile (no swizzle)
-    CUtensorMap map_y;
-    {
-        EncodeTiledFn fn = encode_fn();
-        B200_REQUIRE(fn != nullptr, "lstm_rec_tile: cuTensorMapEncodeTiled is not available from the driver");
-        cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)tiles * (cuuint64_t)T * NB};
-        cuuint64_t strides[1] = {(cuuint64_t)H * 2};
-        cuuint32_t box[2] = {8, (cuuint32_t)SN};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = fn(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)y, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        B200_REQUIRE(r == CUDA_SUCCESS, "lstm_rec_tile: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    }
 #define LAUNCH6(v, e)                                                                                                   \
     do {                                                                                                                \
         B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc6_kernel<v, e>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                              (int)SMEM_BYTES));                                                         \
-        lstm_rec_tc6_kernel<v, e><<<tiles * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, map_y, T, N, reverse);       \
+        lstm_rec_tc6_kernel<v, e><<<tiles * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, (unsigned char*)workspace, T, \
+                                                                               N, reverse);                             \
     } while (0)
     if (variant == 3 && dsmem) LAUNCH6(3, 0);
     else if (variant == 3) LAUNCH6(3, 1);

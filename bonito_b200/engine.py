@@ -360,6 +360,8 @@ class LstmCrfPlan:
                 ya=torch.zeros(nt, T, TB, H, dtype=f16, device=dev),
                 yb=torch.zeros(nt, T, TB, H, dtype=f16, device=dev),
                 gx=torch.zeros(nt, T, self.tile_cs, TB, 4 * H // self.tile_cs, dtype=f16, device=dev),
+                # staging of the recurrent kernel's h all-gather: one region per tile (tiles run concurrently)
+                hx=torch.empty(nt, native.lstm_rec_tile_workspace_bytes(TB), dtype=torch.uint8, device=dev),
                 streams=[torch.cuda.Stream(device=dev) for _ in range(nt)],
                 rec_streams=[torch.cuda.Stream(device=dev, priority=-1) for _ in range(nt)],   # high priority
                 rec_ready=[torch.cuda.Event() for _ in range(nt)], rec_done=[torch.cuda.Event() for _ in range(nt)],
@@ -414,7 +416,8 @@ class LstmCrfPlan:
             i0, cnt = tiles
             n = min(cnt * TB, N - i0 * TB)
             with staged("lstm_rec", st):
-                native.lstm_rec_tile(b["gx"][i0], layer["whh"], dst[i0], T, n, H, layer["reverse"], stream=st)
+                native.lstm_rec_tile(b["gx"][i0], layer["whh"], dst[i0], T, n, H, layer["reverse"], stream=st,
+                                     workspace=b["hx"][i0])
 
         def crf_gemm(src, i, st, max_ctas=0):   # rows r = t*TB + i_chunk of tile i -> out[n0 + i_chunk][t]
             n0 = i * TB

@@ -39,12 +39,14 @@ SIGNATURES = {
     "b200_lstm_rec_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_lstm_tile_chunks": (c_int, [c_int]),
     "b200_lstm_tile_cluster": (c_int, [c_int]),
-    "b200_lstm_rec_tile_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200_lstm_rec_tile_workspace_bytes": (c_size_t, [c_int]),
+    "b200_lstm_rec_tile_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_debug_lstm_tile_timeline": (c_int, [c_void_p, c_int]),
     "b200_debug_tmem_probe": (c_int, [c_void_p, c_void_p]),
     "b200_debug_lstm_timeline": (c_int, [c_void_p, c_int]),
     "b200_debug_lstm_max_clusters": (c_int, []),
     "b200_debug_max_clusters": (c_int, [c_int, c_int, c_int]),
+    "b200_debug_exchange_bench": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_crf_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
@@ -198,11 +200,18 @@ def lstm_tile_cluster(hidden):
     return load().b200_lstm_tile_cluster(hidden)
 
 
-def lstm_rec_tile(gx, whh, y, t, n, hidden, reverse, stream=None):
-    """gx [tiles][T][6][48][256], y [tiles][T][48][H] (see b200_lstm_rec_tile_fwd); n chunks = ceil(n/48) tiles."""
+def lstm_rec_tile_workspace_bytes(n):
+    return load().b200_lstm_rec_tile_workspace_bytes(n)
+
+
+def lstm_rec_tile(gx, whh, y, t, n, hidden, reverse, stream=None, workspace=None):
+    """gx [tiles][T][6][48][256], y [tiles][T][48][H] (see b200_lstm_rec_tile_fwd); n chunks = ceil(n/48) tiles.
+    `workspace`: uint8 tensor of lstm_rec_tile_workspace_bytes(n) bytes (allocated here when omitted)."""
     lib = require()
+    if workspace is None:
+        workspace = torch.empty(lstm_rec_tile_workspace_bytes(n), dtype=torch.uint8, device=y.device)
     with torch.cuda.device(y.device):
-        rc = lib.b200_lstm_rec_tile_fwd(_ptr(gx), _ptr(_f16(whh, "whh")), _ptr(y), t, n, hidden,
+        rc = lib.b200_lstm_rec_tile_fwd(_ptr(gx), _ptr(_f16(whh, "whh")), _ptr(y), _ptr(workspace), t, n, hidden,
                                         int(bool(reverse)), _stream(stream))
     _check(rc, "b200_lstm_rec_tile_fwd")
     return y

@@ -55,7 +55,8 @@ def normalisation(sig, scaling_strategy=None, norm_params=None):
 class Read:
     """What `basecall()` needs (`read_id`, float32 `signal`) plus the bookkeeping the writers use."""
 
-    def __init__(self, read_id, pa_signal, filename="", do_trim=True, scaling_strategy=None, norm_params=None):
+    def __init__(self, read_id, pa_signal, filename="", do_trim=True, scaling_strategy=None, norm_params=None, meta=None):
+        meta = meta or {}
         self.read_id, self.filename = str(read_id), filename
         pa = np.asarray(pa_signal, dtype=np.float32)
         self.num_samples = len(pa)
@@ -63,6 +64,26 @@ class Read:
         self.trimmed_samples = trim(pa, threshold=self.scale * 2.4 + self.shift) if do_trim else 0
         self.template_start = self.trimmed_samples
         self.signal = ((pa[self.trimmed_samples:] - self.shift) / self.scale).astype(np.float32)
+        self.scaling_strategy = (scaling_strategy or {}).get("strategy") or "quantile"
+        # acquisition metadata the SAM tags carry (bonito/reader.py:59-87); .npy reads have none
+        self.run_id, self.mux, self.channel, self.read_number = meta.get("run_id", "unknown"), meta.get("mux", 0), \
+            meta.get("channel", 0), meta.get("read_number", 0)
+        self.start_time, self.duration = meta.get("start_time", ""), meta.get("duration", self.num_samples / 5000.0)
+        self.flow_cell_id, self.device_id, self.sample_id, self.exp_start_time = (
+            meta.get(k, "") for k in ("flow_cell_id", "device_id", "sample_id", "exp_start_time"))
+
+    def readgroup(self, model):
+        """@RG header line (reference: bonito/reader.py:59-73)."""
+        fields = [("ID", f"{self.run_id}_{model}"), ("PL", "ONT"), ("DT", self.exp_start_time), ("PU", self.flow_cell_id),
+                  ("PM", self.device_id), ("LB", self.sample_id), ("SM", self.sample_id),
+                  ("DS", f"run_id={self.run_id} basecall_model={model}")]
+        return "\t".join(["@RG", *[f"{k}:{v}" for k, v in fields]])
+
+    def tagdata(self):
+        """Per-read SAM tags (reference: bonito/reader.py:75-86)."""
+        return [f"mx:i:{self.mux}", f"ch:i:{self.channel}", f"st:Z:{self.start_time}", f"du:f:{self.duration}",
+                f"rn:i:{self.read_number}", f"f5:Z:{self.filename}", f"sm:f:{self.shift}", f"sd:f:{self.scale}",
+                f"sv:Z:{self.scaling_strategy}"]
 
 
 class Reader:

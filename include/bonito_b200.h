@@ -114,12 +114,16 @@ int b200_lstm_rec_fwd(const void* gx, const void* whh, void* y, int t, int n, in
  *                               rows (t, chunk), cb_width = 256, cb_rows = 48, ldc = 256)
  *   whh [4H][H]                 as for b200_lstm_rec_fwd
  *   y   [tiles][T][48][H]       h_t in natural unit order; rows of chunks >= n are not written
+ *   workspace                   b200_lstm_rec_tile_workspace_bytes(n) bytes (72 KB per tile): staging of the h all-gather,
+ *                               which goes through L2 as multicast bulk copies; contents irrelevant, but launches that
+ *                               may run concurrently need distinct workspaces
  * tiles = ceil(n / 48); one launch runs all of them (one cluster each; 22 fit on a B200 at once).
  */
 int b200_lstm_tile_chunks(int hidden);
 int b200_lstm_tile_cluster(int hidden);
-int b200_lstm_rec_tile_fwd(const void* gx, const void* whh, void* y, int t, int n, int hidden, int reverse,
-                           void* stream);
+size_t b200_lstm_rec_tile_workspace_bytes(int n);
+int b200_lstm_rec_tile_fwd(const void* gx, const void* whh, void* y, void* workspace, int t, int n, int hidden,
+                           int reverse, void* stream);
 
 /* Timing aid: as b200_debug_lstm_timeline, for b200_lstm_rec_tile_fwd. */
 int b200_debug_lstm_tile_timeline(long long* host_out, int max_steps);
@@ -158,6 +162,14 @@ int b200_debug_tmem_probe(void* out, void* stream);
 
 /* Number of 8-CTA clusters of the tcgen05 recurrent kernel the current device can hold at once (-1 on error). */
 int b200_debug_lstm_max_clusters(void);
+
+/*
+ * Timing aid: the h all-gather of the tile recurrent kernel without the math (6-CTA clusters, 3 x 8 sender warps per CTA,
+ * 256-byte blocks into the h tiles of all six CTAs every step; see debug_bench.cu for the modes: 0 DSMEM bulk copies,
+ * 2 / 3 multicast bulk copies out of an L2 staging buffer, 4 DSMEM with 2 KB copies).  staging: clusters * 73728 bytes
+ * (device); out: 2 x int64 (device) = cycles of CTA 0, steps.
+ */
+int b200_debug_exchange_bench(int mode, int steps, int delay, int clusters, void* staging, void* out, void* stream);
 
 /* Occupancy query: clusters of `cluster_size` CTAs (`threads` threads, `smem_bytes` dynamic shared memory, one CTA per SM
  * when smem_bytes > half an SM) the current device holds at once; -1 on error.  GPC packing decides (B200: 148 SMs). */

@@ -69,3 +69,31 @@ def test_fastq_writer_filters_and_logs():
     assert w.error is None
     assert fd.getvalue() == "@a\nACGT\n+\n5555\n"
     assert w.log == [("a", 105)]
+
+
+def test_sam_writer_record_layout_and_move_table():
+    """Unaligned SAM text as the reference lays it out (bonito/io.py:136-166,441-456; documentation/SAM.md): flag 4, NM:i:0,
+    RG / qs / ns / ts, the read's tag data and the move table mv:B:c,<stride>,<moves>."""
+    from bonito_b200.io import Writer, encode_moves, sam_record
+    from bonito_b200.reader import Read
+    assert encode_moves(np.array([0, 1, 0, 1, 1], dtype=np.int8), 5) == "5,0,1,0,1,1"      # the reference's doctest
+    assert sam_record("r", "ACGT", "5555", None, tags=["qs:i:20"]) == "r\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\t5555\tNM:i:0\tqs:i:20"
+    read = Read("read7", 100.0 + np.arange(300, dtype=np.float32) % 7, filename="read7.npy", do_trim=False,
+                scaling_strategy={"strategy": "pa"}, norm_params={"standardise": 1, "mean": 100.0, "stdev": 2.0},
+                meta={"run_id": "runA", "channel": 12, "mux": 3, "read_number": 9})
+    res = {"sequence": "ACGTA", "qstring": "55555", "moves": np.array([1, 0, 1, 1, 0, 1, 0, 1], dtype=np.int8), "stride": 6}
+    fd = io.StringIO()
+    w = Writer(iter([(read, res)]), fd=fd, mode="w", groups=[read.readgroup("model_x")], group_key="model_x")
+    w.start(); w.join()
+    assert w.error is None
+    lines = fd.getvalue().rstrip("\n").split("\n")
+    assert lines[0].startswith("@HD\tVN:1.5\tSO:unknown\tob:0.0.2") and lines[1].startswith("@PG\tID:basecaller")
+    assert lines[2].startswith("@RG\tID:runA_model_x\tPL:ONT")
+    f = lines[3].split("\t")
+    assert f[:12] == ["read7", "4", "*", "0", "0", "*", "*", "0", "0", "ACGTA", "55555", "NM:i:0"]
+    tags = f[12:]
+    assert tags[:4] == ["RG:Z:runA_model_x", "qs:i:20", "ns:i:300", "ts:i:0"]
+    assert "mx:i:3" in tags and "ch:i:12" in tags and "rn:i:9" in tags and "f5:Z:read7.npy" in tags and "sv:Z:pa" in tags
+    assert tags[-1] == "mv:B:c,6,1,0,1,1,0,1,0,1"
+    with pytest.raises(ValueError):
+        Writer(iter([]), mode="wb")
