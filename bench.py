@@ -177,21 +177,41 @@ class Ctx:
         return t.tolist()
 
 
-def time_resident(ctx, step, steps, warmup, sampler=None):
-    """W untimed + exactly K timed steps, CUDA events on the launch stream, barrier + synchronize on both sides."""
-    for _ in range(warmup):
-        step(None)
+N_SLOTS = int(os.environ.get("B200_BENCH_SLOTS", "2"))     # batches in flight in the resident loop (as in score_batches)
+
+
+def time_resident(ctx, step, steps, warmup, sampler=None, slots=1):
+    """
+    W untimed + exactly K timed steps, CUDA events on the launch stream, barrier + synchronize on both sides.
+    slots > 1: step i is enqueued on stream i % slots with buffer set i % slots (what score_batches does): consecutive
+    batches overlap on the device; the timed region still contains exactly K complete steps.
+    """
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream(device=ctx.device) for _ in range(slots)] if slots > 1 else [main]
+
+    def run(i, events):
+        if slots == 1:
+            return step(events, 0)
+        with torch.cuda.stream(streams[i % slots]):
+            return step(events, i % slots)
+
+    for i in range(warmup):
+        run(i, None)
     ctx.barrier()
     if sampler is not None:
         sampler.mark_begin()
     events = []
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
+    t0.record(main)
+    for st in streams:
+        st.wait_event(t0)
     h0 = time.perf_counter()
-    for _ in range(steps):
-        step(events)
+    for i in range(steps):
+        run(i, events)
     enqueue_ms = (time.perf_counter() - h0) * 1e3 / steps
-    t1.record()
+    for st in streams:
+        main.wait_stream(st)
+    t1.record(main)
     ctx.barrier()
     if sampler is not None:
         sampler.mark_end()
@@ -241,13 +261,14 @@ def bench_hac(ctx, peaks, sampler):
     T = plan.frames(L)
     qs = model.config["qscore"]
 
-    def step(events):
-        scores = plan.forward(x_dev, events=events)
+    def step(events, slot):
+        scores = plan.forward(x_dev, events=events, slot=slot)
         return _decoder(scores, spec["state_len"], blank_score=plan.blank_score, qscale=qs["scale"], qbias=qs["bias"],
-                        events=events)
+                        events=events, slot=slot)
 
-    elapsed_ms, events, enqueue_ms = time_resident(ctx, step, args.steps, max(args.warmup, 3), sampler)
-    log(f"hac resident: {elapsed_ms / args.steps:.2f} ms/step")
+    slots = N_SLOTS if plan.supports_slots else 1
+    elapsed_ms, events, enqueue_ms = time_resident(ctx, step, args.steps, max(args.warmup, 3), sampler, slots=slots)
+    log(f"hac resident: {elapsed_ms / args.steps:.2f} ms/step ({slots} batches in flight)")
     e2e_ms = time_e2e(ctx, model, host_batch, args.steps, qs)
     for _ in range(2):
         compute_scores(model, host_batch, scale=qs["scale"], offset=qs["bias"])
@@ -309,7 +330,8 @@ def bench_hac(ctx, peaks, sampler):
         "config": {"workload": f"hac-shaped LSTM-CRF (H={H}, {spec['n_lstm']} LSTM, {plan.n_scores} scores/frame), "
                                f"batch {N}/GPU, {CHUNK}->{L}-sample chunks ({T} frames), forward+decode",
                    "weights": "seeded synthetic (bonito_b200/synth.py)", "l2": "per-step tensors (0.16-2.6 GB) exceed the 126 MB L2",
-                   "parallelism": f"chunk-sharded replicas x{world}"},
+                   "parallelism": f"chunk-sharded replicas x{world}",
+                   "batches_in_flight": slots},
         "e2e": {"value": world * N * L * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": N * L * 2, "d2h_bytes_per_step": 3 * N * T, "ms_per_step": e2e_ms / args.steps,
                 "api": "bonito_b200.crf.basecall.score_batches(model, float32 host batches): the loop basecall() runs",
@@ -351,12 +373,12 @@ def bench_sup(ctx, peaks, model, spec, L, steps, warmup, with_e2e=True):
     plan = model.native_plan(device)
     qs = model.config["qscore"]
 
-    def step(events):
-        scores = plan.forward(x_dev, events=events)
+    def step(events, slot):
+        scores = plan.forward(x_dev, events=events, slot=slot)
         return _decoder(scores, spec["state_len"], blank_score=plan.blank_score, qscale=qs["scale"], qbias=qs["bias"],
-                        events=events)
+                        events=events, slot=slot)
 
-    elapsed_ms, events, enqueue_ms = time_resident(ctx, step, steps, warmup)
+    elapsed_ms, events, enqueue_ms = time_resident(ctx, step, steps, warmup, slots=N_SLOTS)
     e2e_ms = time_e2e(ctx, model, host_batch, steps, qs) if with_e2e else 0.0
     elapsed_ms, e2e_ms = ctx.max_over_ranks([elapsed_ms, e2e_ms])
     log(f"sup L={L}: resident {elapsed_ms / steps:.2f} ms/step" + (f", e2e {e2e_ms / steps:.2f}" if with_e2e else ""))

@@ -59,9 +59,12 @@ def compute_scores(model, batch, beam_width=32, beam_cut=100.0, scale=1.0, offse
 
 
 class _Slot:
-    """Staging of one in-flight batch: pinned fp16 input, device input, device + pinned result arrays, two events."""
+    """Staging of one in-flight batch: pinned fp16 input, device input, device + pinned result arrays, two events, and the
+    CUDA stream the batch's kernels are enqueued on (one per slot: consecutive batches overlap on the device)."""
 
-    def __init__(self, shape, device):
+    def __init__(self, shape, device, index=0):
+        self.index = index
+        self.stream = torch.cuda.Stream(device=device)
         self.pinned_in = torch.empty(shape, dtype=torch.float16, pin_memory=True)
         self.dev_in = torch.empty(shape, dtype=torch.float16, device=device)
         self.dev_out = self.pinned_out = None          # uint8 [3, N, T] (moves, sequence, qstring), sized on first use
@@ -74,9 +77,11 @@ def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=
     """
     `compute_scores` over an iterable of (key, float32 host batch), yielding (key, result) in order, as a `depth`-deep
     pipeline: the fp16 cast + H2D copy of batch k+1 (copy stream) and the D2H copy of batch k-1 overlap the kernels of
-    batch k, and the host does not wait for the GPU before the next batch is enqueued.  This is the loop `basecall()` runs
-    (the reference overlaps the same stages with a background thread, bonito/crf/basecall.py:70-72); results are
-    identical to calling `compute_scores` batch by batch.
+    batch k, the host does not wait for the GPU before the next batch is enqueued, and every slot runs on its own CUDA
+    stream with its own buffer set of the native plan, so the kernels of consecutive batches overlap as well (the decode
+    and the GEMMs of one batch fill the SMs the recurrent clusters of the other leave free).  This is the loop
+    `basecall()` runs (the reference overlaps host stages with a background thread, bonito/crf/basecall.py:70-72);
+    results are identical to calling `compute_scores` batch by batch.
     """
     from bonito_b200.decode import _decoder
     device = next(model.parameters()).device
@@ -84,6 +89,9 @@ def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=
         raise RuntimeError("bonito_b200 needs a CUDA device (there is no CPU path)")
     rings, pending = {}, []          # input shape -> [slots, next]; FIFO of slots whose results are not handed out yet
     copy_stream = torch.cuda.Stream(device=device)
+    # several batches in flight need one buffer set of the native plan per slot; plans without slots (the generic-layout
+    # LSTM path of the narrow models) run their batches back to back on the slots' streams
+    multi_slot = _supports_slots(model, device)
 
     def result_of(slot):
         slot.done.synchronize()
@@ -92,24 +100,26 @@ def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=
 
     def enqueue(slot, key, batch):
         with torch.inference_mode(), torch.cuda.device(device):
-            main = torch.cuda.current_stream()
             slot.key = key
             slot.pinned_in.copy_(batch)              # fp32 -> fp16 on the host, as the reference does
             with torch.cuda.stream(copy_stream):
                 slot.dev_in.copy_(slot.pinned_in, non_blocking=True)
                 slot.in_ready.record(copy_stream)
-            main.wait_event(slot.in_ready)
-            scores = model(slot.dev_in)
-            if reverse:
-                scores = _revcomp_native(model, scores, blank_score)
-            n, t, c = scores.shape
-            if slot.dev_out is None:
-                slot.dev_out = torch.empty(3, n, t, dtype=torch.uint8, device=device)
-                slot.pinned_out = torch.empty(3, n, t, dtype=torch.uint8, pin_memory=True)
-            state_len = int(round(np.log(c) / np.log(4))) - 1
-            _decoder(scores, state_len, blank_score=blank_score, qscale=scale, qbias=offset, out=slot.dev_out)
-            slot.pinned_out.copy_(slot.dev_out, non_blocking=True)
-            slot.done.record(main)
+            with torch.cuda.stream(slot.stream):
+                main = slot.stream
+                main.wait_event(slot.in_ready)
+                scores = model(slot.dev_in, slot=slot.index) if multi_slot else model(slot.dev_in)
+                if reverse:
+                    scores = _revcomp_native(model, scores, blank_score)
+                n, t, c = scores.shape
+                if slot.dev_out is None:
+                    slot.dev_out = torch.empty(3, n, t, dtype=torch.uint8, device=device)
+                    slot.pinned_out = torch.empty(3, n, t, dtype=torch.uint8, pin_memory=True)
+                state_len = int(round(np.log(c) / np.log(4))) - 1
+                _decoder(scores, state_len, blank_score=blank_score, qscale=scale, qbias=offset, out=slot.dev_out,
+                         slot=slot.index)
+                slot.pinned_out.copy_(slot.dev_out, non_blocking=True)
+                slot.done.record(main)
 
     for key, batch in batches:
         shape = tuple(batch.shape)
@@ -118,11 +128,16 @@ def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=
                 while pending:
                     yield result_of(pending.pop(0))
                 rings.clear()
-            rings[shape] = [[_Slot(shape, device) for _ in range(depth)], 0]
+            rings[shape] = [[_Slot(shape, device, index=i) for i in range(depth)], 0]
+            if not multi_slot:                       # one shared stream: the batches serialise on the device
+                for sl in rings[shape][0][1:]:
+                    sl.stream = rings[shape][0][0].stream
             # the new device buffers may reuse memory that kernels already enqueued on the compute stream still touch (the
             # caching allocator only orders reuse on the allocating stream): the copy stream must not write them earlier
             with torch.cuda.device(device):
                 copy_stream.wait_stream(torch.cuda.current_stream())
+                for sl in rings[shape][0]:
+                    sl.stream.wait_stream(torch.cuda.current_stream())
         ring = rings[shape]
         slot = ring[0][ring[1]]
         ring[1] = (ring[1] + 1) % depth
@@ -132,6 +147,15 @@ def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=
         pending.append(slot)
     while pending:
         yield result_of(pending.pop(0))
+
+
+def _supports_slots(model, device):
+    """True when the model's native plan keeps independent buffer sets per slot (tile-layout LSTM path, transformer)."""
+    try:
+        plan = model.native_plan(device)
+    except Exception:
+        return False
+    return bool(getattr(plan, "supports_slots", False))
 
 
 def _revcomp_native(model, scores, blank_score):

@@ -109,7 +109,7 @@ class SeqdistModel(Module):
         return cls(**kwargs)
 
     # -- forward -----------------------------------------------------------------------------------
-    def forward(self, x, *args):
+    def forward(self, x, *args, slot=0):
         """
         Plain module tree ([T, N, C+blanks], the reference's non-koi path) unless `use_koi` armed the
         native engine, in which case the result is [N, T, C] fp16 without blank column and any failure to
@@ -122,7 +122,9 @@ class SeqdistModel(Module):
                 raise RuntimeError("bonito_b200: CUDA model called without use_koi(); call model.use_koi(...) "
                                    "(load_model(..., use_koi=True)) or run the module tree on the CPU")
             return self.encoder(x)
-        return self.native_plan(x.device if x.is_cuda else None).forward(x)
+        # `slot`: independent buffer set of the native plan, for callers that keep several batches in flight on
+        # different streams (score_batches)
+        return self.native_plan(x.device if x.is_cuda else None).forward(x, slot=slot)
 
     def native_plan(self, device=None):
         from bonito_b200 import native

@@ -69,7 +69,8 @@ constexpr uint32_t SMEM_BYTES = OFF_BARS + 8 * N_BARS + 64 + 1024;   // ~182 KB:
 
 // timeline of CTA 0 (VARIANT 3), sub-tile 0: per step, SM-clock stamps of
 //   [0] h tile complete (MMA thread)   [1] MMAs issued + committed   [2] accumulator ready (epilogue warp 0)
-//   [3] TMEM loaded   [4] cell update done + staged   [5] h block sent (warp 0)   [6] %globaltimer (ns) at [0]   [7] [5] for warp 7
+//   [3] TMEM loaded   [4] cell update done + staged   [5] h block sent (warp 0)   [6] %globaltimer (ns) at [0]
+//   [7] the MMA warp starts waiting for the h tile (its work of the previous step is issued)
 constexpr int TL_STEPS = 256;
 __device__ long long g_timeline6[TL_STEPS][8];
 
@@ -203,9 +204,9 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned c
             if (tl && ew == 0) g_timeline6[ts][4] = clock64();
             // staging block of this warp for the tile (sub, parity p^1): [k-chunk u0/8][16 chunks][16 B], the h-tile layout
             unsigned char* g = hx + (size_t)((p ^ 1) * NS + sub) * HT + dst_off;
-            if (lane < SN) {   // chunk `lane` of the sub-tile: its 8 units -> Y[t] and -> the staging block
-                const uint4 chunk = reinterpret_cast<const uint4*>(stage)[lane];
-                if (y_ok) *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;
+            uint4 chunk = make_uint4(0, 0, 0, 0);
+            if (lane < SN) {   // chunk `lane` of the sub-tile: its 8 units -> the staging block first (it is on the critical path)
+                chunk = reinterpret_cast<const uint4*>(stage)[lane];
                 if (step + 1 < T) reinterpret_cast<uint4*>(g)[lane] = chunk;
             }
             if (step + 1 < T) {
@@ -215,8 +216,9 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned c
                     bulk_multicast(base + OFF_H + (uint32_t)(sub * 2 + (p ^ 1)) * HT + dst_off, g, STAGE_WARP,
                                    bars.hfull(sub, p ^ 1), (uint16_t)((1u << CS) - 1u));
             }
+            if (y_ok) *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;   // -> Y[t], off the critical path
         }
-        if (tl) g_timeline6[ts][ew == 0 ? 5 : 7] = clock64();
+        if (tl && ew == 0) g_timeline6[ts][5] = clock64();
         __syncwarp();
     }
 }
@@ -314,6 +316,7 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
             for (int sub = 0; sub < NS; ++sub) {
                 if (sub >= nsub) break;
                 const uint32_t hbar = bars.hfull(sub, p);
+                if (VARIANT == 3 && sub == 0 && blockIdx.x == 0 && lane == 0) g_timeline6[step % TL_STEPS][7] = clock64();
                 if (step > 0) mbar_wait(hbar, (uint32_t)((((step + 1) >> 1) - 1) & 1));
                 if (elect_one_sync()) {
                     if (step > 0) {

@@ -204,6 +204,12 @@ class LstmCrfPlan:
             self._bufs[key]["stem"][-tail:].zero_()
         return self._bufs[key]
 
+    @property
+    def supports_slots(self):
+        """Independent buffer sets (several batches in flight) exist for the tile-layout path only."""
+        import os
+        return bool(self.tile) and os.environ.get("B200_LSTM_TILE", "1") != "0"
+
     TILE = 32  # chunks per recurrent cluster
     # CTAs a per-tile GEMM may occupy while recurrent clusters of other tiles are resident (0 = all SMs)
     TILE_GEMM_CTAS = 0
@@ -474,13 +480,13 @@ class LstmCrfPlan:
         return out
 
     def forward(self, x, out=None, gemm_impl=native.GEMM_AUTO, return_features=False, events=None, tiled=None,
-                decode=None):
+                decode=None, slot=0):
         with torch.cuda.device(self.device):    # streams / events / launches belong to the plan's device, whatever is current
             return self._forward(x, out=out, gemm_impl=gemm_impl, return_features=return_features, events=events,
-                                 tiled=tiled, decode=decode)
+                                 tiled=tiled, decode=decode, slot=slot)
 
     def _forward(self, x, out=None, gemm_impl=native.GEMM_AUTO, return_features=False, events=None, tiled=None,
-                 decode=None):
+                 decode=None, slot=0):
         """
         x: [N, 1, L] (or [N, L]) fp16 CUDA -> scores [N, T, C] fp16 (no blank column).
         `events`: optional list; (stage, start, end) CUDA events are appended per kernel.
@@ -492,7 +498,9 @@ class LstmCrfPlan:
             if tiled is None:
                 tiled = (not return_features) and x.shape[0] > self.tile and os.environ.get("B200_TILE_STREAMS", "1") != "0"
             return self.forward_tiles(x, out=out, gemm_impl=gemm_impl, events=events, return_features=return_features,
-                                      streams=tiled)
+                                      streams=tiled, slot=slot)
+        if slot != 0:
+            raise NotImplementedError("several batches in flight (slot != 0) need the tile-layout path (hidden size 384)")
         if tiled is None:
             tiled = (not return_features) and x.shape[0] > self.TILE
         if tiled:
@@ -579,11 +587,11 @@ class CrfDecoder:
     def __init__(self):
         self._ws_by_device = {}     # one workspace per (device, host thread): basecall() decodes on background threads
 
-    def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0, events=None, out=None):
+    def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0, events=None, out=None, slot=0):
         with torch.cuda.device(scores.device):
-            return self._call(scores, state_len, blank_score, qscale, qbias, events, out)
+            return self._call(scores, state_len, blank_score, qscale, qbias, events, out, slot)
 
-    def _call(self, scores, state_len, blank_score, qscale, qbias, events, out):
+    def _call(self, scores, state_len, blank_score, qscale, qbias, events, out, slot=0):
         """-> (moves, sequence, qstring) uint8 [N, T] on the device; `out`: optional uint8 [3, N, T] to write them into."""
         n, t, c = scores.shape
         if c != 4 ** (state_len + 1):
@@ -598,7 +606,7 @@ class CrfDecoder:
         scores = scores.to(torch.float16).contiguous()
         need = native.crf_decode_workspace_bytes(n, t, state_len)
         import threading
-        key = (scores.device, threading.get_ident())
+        key = (scores.device, threading.get_ident(), slot)
         ws = self._ws_by_device.get(key)
         if ws is None or ws.numel() < need:
             ws = self._ws_by_device[key] = torch.empty(need, dtype=torch.uint8, device=scores.device)

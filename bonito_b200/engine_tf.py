@@ -42,6 +42,8 @@ def find_transformer_encoder(encoder):
 
 
 class TransformerPlan:
+    supports_slots = True      # buffers are keyed by (N, L, slot)
+
     def __init__(self, encoder, device):
         from bonito_b200.transformer.model import TransformerEncoderLayer
         enc = find_transformer_encoder(encoder)
@@ -116,10 +118,11 @@ class TransformerPlan:
     def frames(self, L):
         return self._geometry(L)[-1]["lout"] * self.up_factor
 
-    def _buffers(self, N, L):
-        key = (N, L)
+    def _buffers(self, N, L, slot=0):
+        key = (N, L, slot)
         if key not in self._bufs:
-            self._bufs.clear()
+            for k in [k for k in self._bufs if k[:2] != (N, L)]:
+                del self._bufs[k]
             geo = self._geometry(L)
             dev, f16 = self.device, torch.float16
             bufs = dict(geo=geo, act=[])
@@ -143,16 +146,16 @@ class TransformerPlan:
             self._bufs[key] = bufs
         return self._bufs[key]
 
-    def forward(self, x, out=None, events=None, return_features=False, **_):
+    def forward(self, x, out=None, events=None, return_features=False, slot=0, **_):
         with torch.cuda.device(self.device):    # streams / events / launches belong to the plan's device, whatever is current
-            return self._forward(x, out=out, events=events, return_features=return_features)
+            return self._forward(x, out=out, events=events, return_features=return_features, slot=slot)
 
-    def _forward(self, x, out=None, events=None, return_features=False):
+    def _forward(self, x, out=None, events=None, return_features=False, slot=0):
         if x.dim() == 3:
             x = x[:, 0, :]
         x = x.to(device=self.device, dtype=torch.float16).contiguous()
         N, L = x.shape
-        b = self._buffers(N, L)
+        b = self._buffers(N, L, slot)
         geo, T, M, d, ff = b["geo"], b["T"], b["M"], self.d_model, self.d_ff
         feats = {}
 

@@ -29,7 +29,7 @@ last = np.array([max(s for s in range(T) if s % 256 == i) for i in range(256)])
 order = np.argsort(last)
 tl = tl[order]
 s = slice(20, 250)
-names = ["h_full", "mma_issued", "d_full(w0)", "tmem_ld(w0)", "math(w0)", "sent(w0)", None, "sent(w7)"]
+names = ["h_full", "mma_issued", "d_full(w0)", "tmem_ld(w0)", "math(w0)", "sent(w0)", None, None]
 print("cycles per step: %.0f" % np.diff(tl[s, 0]).mean())
 base = tl[s, 0]
 print("SM clock during the kernel: %.0f MHz" % ((tl[250, 0] - tl[20, 0]) / (tl[250, 6] - tl[20, 6]) * 1e3))
@@ -37,5 +37,5 @@ for i, n in enumerate(names):
     if n is None:
         continue
     print("%-12s +%7.0f cycles after h_full" % (n, (tl[s, i] - base).mean()))
-print("next h_full after sent(w0): %.0f ; after sent(w7): %.0f" %
-      ((tl[21:251, 0] - tl[20:250, 5]).mean(), (tl[21:251, 0] - tl[20:250, 7]).mean()))
+print("next h_full after sent(w0): %.0f ; MMA warp waits for h_full(sub 0) for %.0f cycles" %
+      ((tl[21:251, 0] - tl[20:250, 5]).mean(), (tl[s, 0] - tl[s, 7]).mean()))
