@@ -23,27 +23,44 @@
 
 namespace {
 
-__device__ __forceinline__ float lse5(float a, float b, float c, float d, float e) {
-    float m = fmaxf(fmaxf(fmaxf(a, b), fmaxf(c, d)), e);
-    float s = __expf(a - m) + __expf(b - m) + __expf(c - m) + __expf(d - m) + __expf(e - m);
-    return m + __logf(s);
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// log2(sum_i 2^x_i) of five values: one max tree, five bare ex2 and one bare lg2 (the largest term contributes 2^0 = 1, so
+// the sum is in [1, 5] and flushing sub-normal terms to zero changes nothing)
+__device__ __forceinline__ float lse2_5(float a, float b, float c, float d, float e) {
+    const float m = fmaxf(fmaxf(fmaxf(a, b), fmaxf(c, d)), e);
+    const float s = ex2_approx(a - m) + ex2_approx(b - m) + ex2_approx(c - m) + ex2_approx(d - m) + ex2_approx(e - m);
+    return m + lg2_approx(s);
 }
 
 template <int S>
 struct DecodeSmem {
     static constexpr int NW = (S + 31) / 32;
     static constexpr int TB = 16384 / S;                 // back-pointer rows per trace-back block
-    static constexpr size_t kBuf = 0;                                  // float [2][S]
-    static constexpr size_t kVit = kBuf + 2 * S * sizeof(float);       // float [2][S]
-    static constexpr size_t kUnion = kVit + 2 * S * sizeof(float);     // float [2][4*S]  |  u8 [TB][S]
+    static constexpr size_t kAv = 0;                                   // float2 [2][S]: (alpha', Viterbi score) | float [2][S] in pass 1
+    static constexpr size_t kUnion = kAv + 2 * S * sizeof(float2);     // float [2][4*S]  |  u8 [TB][S]
     static constexpr size_t kUnionBytes = (2 * 4 * S * sizeof(float) > (size_t)TB * S) ? 2 * 4 * S * sizeof(float) : (size_t)TB * S;
-    static constexpr size_t kPart = kUnion + kUnionBytes;
-    static constexpr size_t kRed = kPart + 2 * NW * 4 * sizeof(float);
+    static constexpr size_t kPart = kUnion + kUnionBytes;              // float [2][NW][4]
+    static constexpr size_t kKt = kPart + 2 * NW * 4 * sizeof(float);  // float [2]: per-step posterior normaliser
+    static constexpr size_t kRed = kKt + 16;
     static constexpr size_t kRedI = kRed + NW * sizeof(float);
     static constexpr size_t kOut = kRedI + NW * sizeof(int) + 16;      // u8 [3][T]
     static size_t bytes(int T) { return kOut + 3 * (size_t)T + 16; }
 };
 
+template <int V>
+struct IntC { static constexpr int value = V; };
+
+// All recurrences run in the log2 domain (scores are multiplied by log2(e) once when they are loaded): every
+// exponential / logarithm is then a single bare MUFU instruction.  (The first version of this kernel used __expf / __logf
+// in the natural-log domain: 195 + 86 SASS instructions per forward / backward state-step, a third of them the FMUL /
+// FSETP range handling around each MUFU; this one needs ~105 + ~55.)  The step loops are unrolled by two so that every
+// buffer that flips with the step parity is a compile-time address.
 template <int S>
 __global__ void __launch_bounds__(S)
 crf_decode_kernel(const __half* __restrict__ scores, int T, float blank, float qscale, float qbias,
@@ -53,11 +70,12 @@ crf_decode_kernel(const __half* __restrict__ scores, int T, float blank, float q
     using L = DecodeSmem<S>;
     constexpr int Q = S / 4, NW = L::NW, TB = L::TB;
     extern __shared__ __align__(16) unsigned char sm[];
-    float (*buf)[S] = reinterpret_cast<float (*)[S]>(sm + L::kBuf);
-    float (*vit)[S] = reinterpret_cast<float (*)[S]>(sm + L::kVit);
+    float (*buf)[S] = reinterpret_cast<float (*)[S]>(sm + L::kAv);            // pass 1: beta'
+    float2 (*av)[S] = reinterpret_cast<float2 (*)[S]>(sm + L::kAv);           // pass 2: (alpha', Viterbi)
     float (*msh)[4 * S] = reinterpret_cast<float (*)[4 * S]>(sm + L::kUnion);
     uint8_t (*bp_blk)[S] = reinterpret_cast<uint8_t (*)[S]>(sm + L::kUnion);
     float (*part)[NW][4] = reinterpret_cast<float (*)[NW][4]>(sm + L::kPart);
+    float* kt_sh = reinterpret_cast<float*>(sm + L::kKt);
     float* red = reinterpret_cast<float*>(sm + L::kRed);
     int* red_i = reinterpret_cast<int*>(sm + L::kRedI);
     uint8_t* out_sh = sm + L::kOut;
@@ -71,240 +89,24 @@ crf_decode_kernel(const __half* __restrict__ scores, int T, float blank, float q
     double* bsum = ws_bsum + (size_t)n * (T + 1);
     uint8_t* bp = ws_bp + (size_t)n * T * S;
     float* pm = ws_pm + (size_t)n * T * 4;
-
-    // Scatter the 4 in-edge move scores of state s to their consumers in the backward pass:
-    // in-edge j of s leaves predecessor p = j*Q + s/4 as its b = s%4 -th out-edge -> msh[4p+b] = msh[j*S+s].
-    auto scatter = [&](float* dst, uint2 raw) {
-        const __half2 m01 = *reinterpret_cast<const __half2*>(&raw.x);
-        const __half2 m23 = *reinterpret_cast<const __half2*>(&raw.y);
-        dst[0 * S + s] = __low2float(m01);
-        dst[1 * S + s] = __high2float(m01);
-        dst[2 * S + s] = __low2float(m23);
-        dst[3 * S + s] = __high2float(m23);
-    };
+    const float blank2 = blank * LOG2E;
 
     // ---------------- pass 1: backward ----------------
+    // beta'_t[p] = log2-sum over the out-edges of p (stay, and the moves into the four successors 4(p%Q)+c), re-centred on
+    // state 0 of the previous step; the accumulated shifts are kept in fp64 by thread 0 (bsum).
     {
         buf[0][s] = 0.f;
         beta[(size_t)T * S + s] = 0.f;
         if (s == 0) bsum[T] = 0.0;
-        scatter(msh[(T - 1) & 1], sc[(size_t)(T - 1) * S]);
-        uint2 raw_next = (T > 1) ? sc[(size_t)(T - 2) * S] : make_uint2(0, 0);
-        double acc_shift = 0.0;
-        int cur = 0;
-        __syncthreads();
-        for (int t = T - 1; t >= 0; --t) {
-            if (t > 0) scatter(msh[(t - 1) & 1], raw_next);
-            if (t > 1) raw_next = sc[(size_t)(t - 2) * S];
-            const float b0 = buf[cur][0];
-            const float4 mv = *reinterpret_cast<const float4*>(&msh[t & 1][4 * s]);
-            const float4 bs = *reinterpret_cast<const float4*>(&buf[cur][4 * (s % Q)]);
-            const float stay = blank + buf[cur][s] - b0;
-            const float v = lse5(stay, mv.x + bs.x - b0, mv.y + bs.y - b0, mv.z + bs.z - b0, mv.w + bs.w - b0);
-            acc_shift += (double)b0;
-            buf[cur ^ 1][s] = v;
-            beta[(size_t)t * S + s] = v;
-            if (s == 0) bsum[t] = acc_shift;
-            cur ^= 1;
-            __syncthreads();
-        }
-        // logZ = bsum[0] + LSE_s beta'_0[s]
-        const float v = buf[cur][s];
-        float mx = v;
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) red[warp] = mx;
-        __syncthreads();
-        mx = red[0];
-        for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red[w]);
-        __syncthreads();
-        float ex = __expf(v - mx);
-        for (int o = 16; o > 0; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
-        if (lane == 0) red[warp] = ex;
-        __syncthreads();
-        if (s == 0) {
-            float tot = 0.f;
-            for (int w = 0; w < NW; ++w) tot += red[w];
-            logz_sh = mx + __logf(tot);
-        }
-        __syncthreads();
-    }
-
-    // ---------------- pass 2: forward + posteriors + Viterbi ----------------
-    {
-        const double logz = bsum[0] + (double)logz_sh;
-        const int pq = s / 4;  // predecessor along in-edge 1+j is j*Q + pq
-        buf[0][s] = 0.f;
-        vit[0][s] = 0.f;
-        double asum = 0.0;
-        __syncthreads();
-        int cur = 0;
-        uint2 mraw = sc[0];
-        float bnext = beta[(size_t)1 * S + s], bnext0 = beta[(size_t)1 * S];
-        double bs_next = bsum[1];
-        for (int t = 0; t < T; ++t) {
-            uint2 mraw_n = make_uint2(0, 0);
-            float bn_n = 0.f, bn0_n = 0.f;
-            double bsn_n = 0.0;
-            if (t + 1 < T) {  // prefetch: none of this depends on the recurrence
-                mraw_n = sc[(size_t)(t + 1) * S];
-                bn_n = beta[(size_t)(t + 2) * S + s];
-                bn0_n = beta[(size_t)(t + 2) * S];
-                bsn_n = bsum[t + 2];
-            }
-            const __half2 m01 = *reinterpret_cast<const __half2*>(&mraw.x);
-            const __half2 m23 = *reinterpret_cast<const __half2*>(&mraw.y);
-            const float ms[5] = {blank, __low2float(m01), __high2float(m01), __low2float(m23), __high2float(m23)};
-            const float a0 = buf[cur][0];
-            const float v0 = vit[cur][0];
-            float ap[5], vp[5];
-            ap[0] = buf[cur][s] - a0;
-            vp[0] = vit[cur][s] - v0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                ap[1 + j] = buf[cur][j * Q + pq] - a0;
-                vp[1 + j] = vit[cur][j * Q + pq] - v0;
-            }
-            // per-step normaliser (identical in every thread)
-            const float kt = (float)((double)a0 + asum + (double)bnext0 + bs_next - logz);
-            const float bshift = bnext - bnext0 + kt;
-            float x[5], best = -INFINITY, mass = 0.f;
-            int arg = 0;
-#pragma unroll
-            for (int e = 0; e < 5; ++e) {
-                x[e] = ap[e] + ms[e];
-                const float post = __expf(x[e] + bshift);
-                if (e > 0) mass += post;
-                const float cand = __logf(post + 1e-8f) + vp[e];
-                if (cand > best) { best = cand; arg = e; }
-            }
-            const float anew = lse5(x[0], x[1], x[2], x[3], x[4]);
-            asum += (double)a0;
-            buf[cur ^ 1][s] = anew;
-            vit[cur ^ 1][s] = best;
-            bp[(size_t)t * S + s] = (uint8_t)arg;
-            // move mass per emitted base (s % 4): reduce lanes of equal lane%4
-            mass += __shfl_xor_sync(0xffffffffu, mass, 4);
-            mass += __shfl_xor_sync(0xffffffffu, mass, 8);
-            mass += __shfl_xor_sync(0xffffffffu, mass, 16);
-            if (lane < 4) part[t & 1][warp][lane] = mass;
-            cur ^= 1;
-            mraw = mraw_n; bnext = bn_n; bnext0 = bn0_n; bs_next = bsn_n;
-            __syncthreads();
-            if (s < 4) {
-                float tot = 0.f;
-                for (int w = 0; w < NW; ++w) tot += part[t & 1][w][s];
-                pm[(size_t)t * 4 + s] = tot;
-            }
-        }
-        // best final state: max Viterbi score, lowest state on ties
-        float v = vit[cur][s];
-        int idx = s;
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-        }
-        if (lane == 0) { red[warp] = v; red_i[warp] = idx; }
-        __syncthreads();
-    }
-
-    // ---------------- pass 3: trace-back ----------------
-    {
-        uint8_t* o_mov = out_sh;
-        uint8_t* o_seq = out_sh + T;
-        uint8_t* o_q = out_sh + 2 * T;
-        int state = 0;
-        if (s == 0) {
-            float v = red[0];
-            state = red_i[0];
-            for (int w = 1; w < NW; ++w)
-                if (red[w] > v) { v = red[w]; state = red_i[w]; }
-        }
-        for (int hi = T; hi > 0; hi -= TB) {
-            const int lo = max(hi - TB, 0), rows = hi - lo;
-            __syncthreads();
-            for (int i = s; i < rows * (S / 16); i += S) {
-                const int row = i / (S / 16), c = i % (S / 16);
-                *reinterpret_cast<uint4*>(&bp_blk[row][c * 16]) =
-                    *reinterpret_cast<const uint4*>(bp + (size_t)(lo + row) * S + c * 16);
-            }
-            __syncthreads();
-            if (s == 0) {
-                for (int t = hi - 1; t >= lo; --t) {
-                    const int e = bp_blk[t - lo][state];
-                    const int base = state & 3;
-                    if (e != 0) {
-                        const float p = pm[(size_t)t * 4 + base];
-                        const float err = fmaxf(1.0f - p, 1e-4f);
-                        const float qv = -10.0f * log10f(err) * qscale + qbias;
-                        int qi = (int)rintf(qv) + 33;
-                        qi = min(max(qi, 33), 126);
-                        o_mov[t] = 1;
-                        o_seq[t] = (uint8_t)("ACGT"[base]);
-                        o_q[t] = (uint8_t)qi;
-                        state = (e - 1) * Q + (state >> 2);
-                    } else {
-                        o_mov[t] = 0; o_seq[t] = 0; o_q[t] = 0;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (int t = s; t < T; t += S) {
-            moves[(size_t)n * T + t] = o_mov[t];
-            seq[(size_t)n * T + t] = o_seq[t];
-            qual[(size_t)n * T + t] = o_q[t];
-        }
-    }
-}
-
-// ---- v2: the same arithmetic, step loops unrolled by two ---------------------------------------------------------------
-// Every buffer that flips with the step parity (buf, vit, msh, part) is indexed by a compile-time constant inside a step
-// body instantiated for parity 0 and 1, and the global-memory cursors are running pointers: about a third of the v1 loop
-// was address arithmetic.  Results are bit-identical to v1 (same operations in the same order).
-template <int V>
-struct IntC { static constexpr int value = V; };
-
-template <int S>
-__global__ void __launch_bounds__(S)
-crf_decode_kernel_v2(const __half* __restrict__ scores, int T, float blank, float qscale, float qbias,
-                     float* __restrict__ ws_beta, double* __restrict__ ws_bsum, uint8_t* __restrict__ ws_bp,
-                     float* __restrict__ ws_pm, uint8_t* __restrict__ moves, uint8_t* __restrict__ seq,
-                     uint8_t* __restrict__ qual) {
-    using L = DecodeSmem<S>;
-    constexpr int Q = S / 4, NW = L::NW, TB = L::TB;
-    extern __shared__ __align__(16) unsigned char sm[];
-    float (*buf)[S] = reinterpret_cast<float (*)[S]>(sm + L::kBuf);
-    float (*vit)[S] = reinterpret_cast<float (*)[S]>(sm + L::kVit);
-    float (*msh)[4 * S] = reinterpret_cast<float (*)[4 * S]>(sm + L::kUnion);
-    uint8_t (*bp_blk)[S] = reinterpret_cast<uint8_t (*)[S]>(sm + L::kUnion);
-    float (*part)[NW][4] = reinterpret_cast<float (*)[NW][4]>(sm + L::kPart);
-    float* red = reinterpret_cast<float*>(sm + L::kRed);
-    int* red_i = reinterpret_cast<int*>(sm + L::kRedI);
-    uint8_t* out_sh = sm + L::kOut;
-    __shared__ float logz_sh;
-
-    const int n = blockIdx.x;
-    const int s = threadIdx.x;
-    const int lane = s & 31, warp = s >> 5;
-    const uint2* sc = reinterpret_cast<const uint2*>(scores + (size_t)n * T * S * 4) + s;  // row stride S
-    float* beta = ws_beta + (size_t)n * (T + 1) * S;
-    double* bsum = ws_bsum + (size_t)n * (T + 1);
-    uint8_t* bp = ws_bp + (size_t)n * T * S;
-    float* pm = ws_pm + (size_t)n * T * 4;
-
-    // ---------------- pass 1: backward ----------------
-    {
-        buf[0][s] = 0.f;
-        beta[(size_t)T * S + s] = 0.f;
-        if (s == 0) bsum[T] = 0.0;
-        {
-            const uint2 raw = sc[(size_t)(T - 1) * S];
-            const __half2 m01 = *reinterpret_cast<const __half2*>(&raw.x);
-            const __half2 m23 = *reinterpret_cast<const __half2*>(&raw.y);
-            msh[0][0 * S + s] = __low2float(m01); msh[0][1 * S + s] = __high2float(m01);
-            msh[0][2 * S + s] = __low2float(m23); msh[0][3 * S + s] = __high2float(m23);
-        }
+        // scatter the 4 in-edge move scores of state s to their consumers: in-edge j of s leaves predecessor
+        // p = j*Q + s/4 as its b = s%4 -th out-edge -> msh[4p+b] = msh[j*S+s]
+        auto scatter = [&](float* dst, uint2 raw) {
+            const float2 m01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 m23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            dst[0 * S + s] = m01.x * LOG2E; dst[1 * S + s] = m01.y * LOG2E;
+            dst[2 * S + s] = m23.x * LOG2E; dst[3 * S + s] = m23.y * LOG2E;
+        };
+        scatter(msh[0], sc[(size_t)(T - 1) * S]);
         uint2 raw_next = (T > 1) ? sc[(size_t)(T - 2) * S] : make_uint2(0, 0);
         const uint2* sc_pf = sc + (size_t)(T - 3) * S;        // next prefetch: row t-2 of the step being processed
         float* beta_p = beta + (size_t)(T - 1) * S + s;
@@ -313,31 +115,29 @@ crf_decode_kernel_v2(const __half* __restrict__ scores, int T, float blank, floa
         __syncthreads();
         auto bwd = [&](int t, auto cur_c) {
             constexpr int CUR = decltype(cur_c)::value;
-            if (t > 0) {
-                const __half2 m01 = *reinterpret_cast<const __half2*>(&raw_next.x);
-                const __half2 m23 = *reinterpret_cast<const __half2*>(&raw_next.y);
-                msh[CUR ^ 1][0 * S + s] = __low2float(m01); msh[CUR ^ 1][1 * S + s] = __high2float(m01);
-                msh[CUR ^ 1][2 * S + s] = __low2float(m23); msh[CUR ^ 1][3 * S + s] = __high2float(m23);
-            }
+            if (t > 0) scatter(msh[CUR ^ 1], raw_next);
             if (t > 1) raw_next = *sc_pf;
             sc_pf -= S;
             const float b0 = buf[CUR][0];
             const float4 mv = *reinterpret_cast<const float4*>(&msh[CUR][4 * s]);
             const float4 bs = *reinterpret_cast<const float4*>(&buf[CUR][4 * (s % Q)]);
-            const float stay = blank + buf[CUR][s] - b0;
-            const float v = lse5(stay, mv.x + bs.x - b0, mv.y + bs.y - b0, mv.z + bs.z - b0, mv.w + bs.w - b0);
-            acc_shift += (double)b0;
+            const float v = lse2_5(blank2 + buf[CUR][s], mv.x + bs.x, mv.y + bs.y, mv.z + bs.z, mv.w + bs.w) - b0;
             buf[CUR ^ 1][s] = v;
             *beta_p = v;
             beta_p -= S;
-            if (s == 0) *bsum_p = acc_shift;
+            if (warp == 0) {
+                if (lane == 0) {
+                    acc_shift += (double)b0;
+                    *bsum_p = acc_shift;
+                }
+            }
             --bsum_p;
             __syncthreads();
         };
         int t = T - 1;
         for (; t >= 1; t -= 2) { bwd(t, IntC<0>()); bwd(t - 1, IntC<1>()); }
         if (t == 0) bwd(0, IntC<0>());
-        // logZ = bsum[0] + LSE_s beta'_0[s]
+        // log2 Z = bsum[0] + log2-sum_s beta'_0[s]
         const float v = buf[T & 1][s];
         float mx = v;
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -346,84 +146,97 @@ crf_decode_kernel_v2(const __half* __restrict__ scores, int T, float blank, floa
         mx = red[0];
         for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red[w]);
         __syncthreads();
-        float ex = __expf(v - mx);
+        float ex = ex2_approx(v - mx);
         for (int o = 16; o > 0; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
         if (lane == 0) red[warp] = ex;
         __syncthreads();
         if (s == 0) {
             float tot = 0.f;
             for (int w = 0; w < NW; ++w) tot += red[w];
-            logz_sh = mx + __logf(tot);
+            logz_sh = mx + lg2_approx(tot);
         }
         __syncthreads();
     }
 
     // ---------------- pass 2: forward + posteriors + Viterbi ----------------
+    // Rows are stored re-centred: alpha'_{t+1}[s] = log2-sum_e(alpha'_t[pred] + M_t[s,e]) - alpha'_t[0], so the true
+    // alpha_t = alpha'_t + asum_t with asum_{t+1} = asum_t + alpha'_t[0]; likewise beta_t = beta'_t + bsum[t].  The
+    // posterior of edge (s, e) at step t is 2^(alpha'_t[pred] + M_t[s,e] + beta'_{t+1}[s] + k_t) with the per-step normaliser
+    //   k_t = asum_t + bsum[t+1] - log2 Z,
+    // computed in fp64 by thread 0 one step ahead (exact to fp32 rounding however long the chunk is) and broadcast
+    // through shared memory.
     {
         const double logz = bsum[0] + (double)logz_sh;
         const int pq = s / 4;  // predecessor along in-edge 1+j is j*Q + pq
-        buf[0][s] = 0.f;
-        vit[0][s] = 0.f;
-        double asum = 0.0;
+        av[0][s] = make_float2(0.f, 0.f);
+        double asum = 0.0;     // thread 0: sum of the alpha' re-centring shifts before step t
+        if (s == 0) kt_sh[0] = (float)(bsum[1] - logz);       // step 0: alpha'_0 = 0, asum = 0
         __syncthreads();
         uint2 mraw = sc[0];
-        float bnext = beta[(size_t)1 * S + s], bnext0 = beta[(size_t)1 * S];
-        double bs_next = bsum[1];
-        const uint2* sc_p = sc + S;                       // row t+1
-        const float* beta_p = beta + (size_t)2 * S;       // row t+2
-        const double* bsum_p = bsum + 2;
+        float bnext = beta[(size_t)1 * S + s];
+        double bs_next2 = (T > 1 && s == 0) ? bsum[2] : 0.0;   // thread 0: bsum[t+2], for the normaliser of step t+1
+        const uint2* sc_p = sc + S;                           // row t+1
+        const float* beta_p = beta + (size_t)2 * S + s;       // row t+2
+        const double* bsum_p = bsum + 3;
         uint8_t* bp_p = bp + s;
-        float* pm_p = pm + s;                             // used by threads 0..3
+        float* pm_p = pm + s;                                 // used by threads 0..3
         auto fwd = [&](int t, auto cur_c) {
             constexpr int CUR = decltype(cur_c)::value;
             uint2 mraw_n = make_uint2(0, 0);
-            float bn_n = 0.f, bn0_n = 0.f;
-            double bsn_n = 0.0;
+            float bn_n = 0.f;
+            double bs_n = 0.0;
             if (t + 1 < T) {  // prefetch: none of this depends on the recurrence
                 mraw_n = *sc_p;
-                bn_n = beta_p[s];
-                bn0_n = beta_p[0];
-                bsn_n = *bsum_p;
+                bn_n = *beta_p;
+                if (s == 0 && t + 2 < T) bs_n = *bsum_p;
             }
             sc_p += S; beta_p += S; ++bsum_p;
-            const __half2 m01 = *reinterpret_cast<const __half2*>(&mraw.x);
-            const __half2 m23 = *reinterpret_cast<const __half2*>(&mraw.y);
-            const float ms[5] = {blank, __low2float(m01), __high2float(m01), __low2float(m23), __high2float(m23)};
-            const float a0 = buf[CUR][0];
-            const float v0 = vit[CUR][0];
-            float ap[5], vp[5];
-            ap[0] = buf[CUR][s] - a0;
-            vp[0] = vit[CUR][s] - v0;
+            const float2 m01 = __half22float2(*reinterpret_cast<const __half2*>(&mraw.x));
+            const float2 m23 = __half22float2(*reinterpret_cast<const __half2*>(&mraw.y));
+            const float2 a0v0 = av[CUR][0];
+            const float kt = kt_sh[CUR];
+            float2 p[5];
+            p[0] = av[CUR][s];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                ap[1 + j] = buf[CUR][j * Q + pq] - a0;
-                vp[1 + j] = vit[CUR][j * Q + pq] - v0;
-            }
-            // per-step normaliser (identical in every thread)
-            const float kt = (float)((double)a0 + asum + (double)bnext0 + bs_next - logz);
-            const float bshift = bnext - bnext0 + kt;
-            float x[5], best = -INFINITY, mass = 0.f;
+            for (int j = 0; j < 4; ++j) p[1 + j] = av[CUR][j * Q + pq];
+            float x[5];
+            x[0] = p[0].x + blank2;
+            x[1] = fmaf(m01.x, LOG2E, p[1].x);
+            x[2] = fmaf(m01.y, LOG2E, p[2].x);
+            x[3] = fmaf(m23.x, LOG2E, p[3].x);
+            x[4] = fmaf(m23.y, LOG2E, p[4].x);
+            // log2-sum of the five in-edges; its exponentials 2^(x_e - m) are shared with the posteriors:
+            //   post_e = 2^(x_e + beta'_{t+1}[s] + k_t) = 2^(x_e - m) * 2^(m + beta'_{t+1}[s] + k_t)      (12 MUFU per state-step, not 16)
+            const float m = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), x[4]);
+            const float g = ex2_approx(m + bnext + kt);
+            float best = -INFINITY, mass = 0.f, esum = 0.f;
             int arg = 0;
 #pragma unroll
             for (int e = 0; e < 5; ++e) {
-                x[e] = ap[e] + ms[e];
-                const float post = __expf(x[e] + bshift);
+                const float ee = ex2_approx(x[e] - m);
+                esum += ee;
+                const float post = ee * g;
                 if (e > 0) mass += post;
-                const float cand = __logf(post + 1e-8f) + vp[e];
+                const float cand = lg2_approx(post + 1e-8f) + p[e].y;
                 if (cand > best) { best = cand; arg = e; }
             }
-            const float anew = lse5(x[0], x[1], x[2], x[3], x[4]);
-            asum += (double)a0;
-            buf[CUR ^ 1][s] = anew;
-            vit[CUR ^ 1][s] = best;
+            const float anew = m + lg2_approx(esum) - a0v0.x;
+            av[CUR ^ 1][s] = make_float2(anew, best - a0v0.y);
             *bp_p = (uint8_t)arg;
             bp_p += S;
+            if (warp == 0) {   // (warp-uniform branch: the fp64 arithmetic below is issued by one warp only)
+                if (lane == 0) {   // normaliser of step t+1: k_{t+1} = asum_{t+1} + bsum[t+2] - log2 Z, asum_{t+1} = asum_t + alpha'_t[0]
+                    asum += (double)a0v0.x;
+                    kt_sh[CUR ^ 1] = (float)(asum + bs_next2 - logz);
+                    bs_next2 = bs_n;
+                }
+            }
             // move mass per emitted base (s % 4): reduce lanes of equal lane%4
             mass += __shfl_xor_sync(0xffffffffu, mass, 4);
             mass += __shfl_xor_sync(0xffffffffu, mass, 8);
             mass += __shfl_xor_sync(0xffffffffu, mass, 16);
             if (lane < 4) part[CUR][warp][lane] = mass;
-            mraw = mraw_n; bnext = bn_n; bnext0 = bn0_n; bs_next = bsn_n;
+            mraw = mraw_n; bnext = bn_n;
             __syncthreads();
             if (s < 4) {
                 float tot = 0.f;
@@ -437,7 +250,7 @@ crf_decode_kernel_v2(const __half* __restrict__ scores, int T, float blank, floa
         for (; t + 1 < T; t += 2) { fwd(t, IntC<0>()); fwd(t + 1, IntC<1>()); }
         if (t < T) fwd(t, IntC<0>());
         // best final state: max Viterbi score, lowest state on ties
-        float v = vit[T & 1][s];
+        float v = av[T & 1][s].y;
         int idx = s;
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, v, o);
@@ -448,7 +261,7 @@ crf_decode_kernel_v2(const __half* __restrict__ scores, int T, float blank, floa
         __syncthreads();
     }
 
-    // ---------------- pass 3: trace-back (as v1) ----------------
+    // ---------------- pass 3: trace-back ----------------
     {
         uint8_t* o_mov = out_sh;
         uint8_t* o_seq = out_sh + T;
@@ -515,8 +328,7 @@ int launch_decode(const __half* scores, int N, int T, float blank, float qscale,
         const size_t want = (size_t)atoi(pad) * 1024;
         if (want > dyn && want <= 200 * 1024) dyn = want;
     }
-    const char* impl = getenv("B200_DECODE_IMPL");     // "v1": the original step loops; default: unrolled by two
-    auto kern = (impl && impl[0] == 'v' && impl[1] == '1') ? crf_decode_kernel<S> : crf_decode_kernel_v2<S>;
+    auto kern = crf_decode_kernel<S>;
     B200_REQUIRE(dyn <= 200 * 1024, "crf_decode: chunk of %d frames needs %zu B of shared memory", T, dyn);
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     kern<<<N, S, dyn, stream>>>(scores, T, blank, qscale, qbias, beta, bsum, bp, pm, moves, seq, qual);

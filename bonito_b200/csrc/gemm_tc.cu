@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -31,7 +33,8 @@ struct TcSmem {
     static constexpr uint32_t kEpi = STAGES * kStage;             // 8 epilogue warps x (32 rows x 64 B) transpose buffers
     static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;    // 8 x 512 B: the tile's bias slice, one copy per warp
     static constexpr uint32_t kBars = kBias + EPI_WARPS * 512;    // mbarriers after the buffers
-    static constexpr uint32_t kTotal = kBars + 256 + 1024;   // + alignment slack
+    static constexpr uint32_t kTileQ = kBars + 160;               // dynamic tile queue: TQ mbarriers + TQ ints
+    static constexpr uint32_t kTotal = kBars + 384 + 1024;   // + alignment slack
 };
 
 // ---- PTX wrappers not shared with the other tcgen05 kernels -----------------------------------
@@ -44,6 +47,37 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     tc_ld_32x32b_x32(taddr, v);
     tc_wait_ld();
+}
+
+// ---- dynamic tile scheduling -------------------------------------------------------------------------------------
+// The kernels are persistent (one CTA per SM), but the engine runs them next to recurrent clusters that hold 66-132 of the
+// 148 SMs for milliseconds: with a static tile -> CTA assignment the CTAs that cannot be placed before those clusters
+// retire would hold back the whole GEMM.  Tiles are therefore handed out by a ticket counter in global memory
+// (atomicAdd by the TMA-producer thread, one tile ahead); the ticket travels to the MMA and epilogue warps through a
+// small shared-memory queue.  CTAs that start late find the counter exhausted and leave at once.  The counters come
+// from a zero-initialised pool; the last CTA to finish resets the ones its launch used.
+constexpr int TQ = 8;   // queue depth; the producer is never more than 3 tiles ahead of the slowest epilogue warp
+
+struct TileQueue {
+    uint32_t bars;          // TQ mbarriers (shared-memory address)
+    volatile int* tiles;    // TQ tile indices (generic pointer)
+    __device__ __forceinline__ void publish(int q, int tile) const {   // producer thread
+        tiles[q & (TQ - 1)] = tile;
+        mbar_arrive(bars + 8u * (uint32_t)(q & (TQ - 1)));             // release: the store above is visible to the waiters
+    }
+    __device__ __forceinline__ int take(int q) const {                 // any consumer thread
+        mbar_wait(bars + 8u * (uint32_t)(q & (TQ - 1)), (uint32_t)((q / TQ) & 1));
+        return tiles[q & (TQ - 1)];
+    }
+};
+
+// last CTA out resets the `n_ctr` ticket counters and the exit counter behind them
+__device__ __forceinline__ void release_tile_counters(int* ctr, int n_ctr) {
+    const int done = atomicAdd(&ctr[n_ctr], 1);
+    if (done == (int)gridDim.x - 1) {
+        for (int i = 0; i <= n_ctr; ++i) ctr[i] = 0;
+        __threadfence();
+    }
 }
 
 // One warp copies the BN bias values of column block `nb` into its shared-memory slice (zeros when there is no bias).
@@ -167,7 +201,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep) {
+               __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep, int* __restrict__ ctr) {
     using S = TcSmem<BN>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
@@ -178,6 +212,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
     unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    TileQueue tq;
+    tq.bars = base + S::kTileQ;
+    tq.tiles = reinterpret_cast<volatile int*>(gen_base + S::kTileQ + 8 * TQ);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
@@ -195,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(tfull_bar(s), 1);
             mbar_init(tempty_bar(s), EPI_WARPS);  // one arrive per epilogue warp
         }
+        for (int s = 0; s < TQ; ++s) mbar_init(tq.bars + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -212,7 +250,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (elect_one_sync()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            int tile = atomicAdd(ctr, 1);
+            for (int q = 0;; ++q) {
+                tq.publish(q, tile < tiles ? tile : -1);
+                if (tile >= tiles) break;
+                const int next = atomicAdd(ctr, 1);        // its latency hides behind the loads below
                 const int mb = tile / n_blocks, nb = tile % n_blocks;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
@@ -221,6 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tma_load_2d(base + stage * S::kStage + S::kA, &map_b, full_bar(stage), kb * BK, nb * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                tile = next;
             }
         }
     } else if (warp == 1) {
@@ -230,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (int q = 0; tq.take(q) >= 0; ++q) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -258,7 +301,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + ew * 512);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int q = 0;; ++q) {
+            const int tile = tq.take(q);
+            if (tile < 0) break;
             const int mb = tile / n_blocks, nb = tile % n_blocks;
             stage_bias<BN>(sbias, ep.bias, nb, N, lane);   // before the wait: its latency hides behind the mainloop
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -277,6 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base),
                      "r"((uint32_t)(2 * BN)));
     }
+    if (threadIdx.x == 0) release_tile_counters(ctr, 1);
 }
 
 // ---- weight-stationary variant ---------------------------------------------------------------------
@@ -293,13 +339,14 @@ struct WsSmem {
     static constexpr uint32_t kEpi = kRing + WS_STAGES * BM * BK * 2;     // 8 x 2 KB transpose buffers
     static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;            // 8 x 512 B bias slice copies
     static constexpr uint32_t kBars = kBias + EPI_WARPS * 512;
-    static constexpr uint32_t kTotal = kBars + 256 + 1024;
+    static constexpr uint32_t kTileQ = kBars + 160;                       // dynamic tile queue: TQ mbarriers + TQ ints
+    static constexpr uint32_t kTotal = kBars + 384 + 1024;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep) {
+               __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep, int* __restrict__ ctr) {
     using S = WsSmem<BN>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -311,12 +358,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t bres_bar = bars + 8u * (2 * WS_STAGES + 4);
     const uint32_t tmem_slot = bars + 8u * (2 * WS_STAGES + 5);
     unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    TileQueue tq;
+    tq.bars = base + S::kTileQ;
+    tq.tiles = reinterpret_cast<volatile int*>(gen_base + S::kTileQ + 8 * TQ);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
     const int k_blocks = (K + BK - 1) / BK;
-    const int nb = blockIdx.x % n_blocks;                 // this CTA's column block, for its whole life
-    const int mb0 = blockIdx.x / n_blocks, mb_step = gridDim.x / n_blocks;
+    const int nb = blockIdx.x % n_blocks;                 // this CTA's column block, for its whole life; row blocks by ticket
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a));
@@ -330,6 +379,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(tempty_bar(s), EPI_WARPS);
         }
         mbar_init(bres_bar, 1);
+        for (int s = 0; s < TQ; ++s) mbar_init(tq.bars + 8u * s, 1);
         mbar_fence_init();
     }
     if (warp == 1) tc_alloc(tmem_slot, BN <= 128 ? 256 : 512);
@@ -341,18 +391,25 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         // ===== TMA producer: B once, then A tiles =====
         if (elect_one_sync()) {
-            mbar_expect_tx(bres_bar, (uint32_t)k_blocks * BN * 128);
-            for (int kb = 0; kb < k_blocks; ++kb)
-                tma_load_2d(base + S::kBres + kb * (BN * 128), &map_b, bres_bar, kb * BK, nb * BN);
+            int mb = atomicAdd(&ctr[nb], 1);
+            if (mb < m_blocks) {      // a CTA that starts after the column block is exhausted does not even load B
+                mbar_expect_tx(bres_bar, (uint32_t)k_blocks * BN * 128);
+                for (int kb = 0; kb < k_blocks; ++kb)
+                    tma_load_2d(base + S::kBres + kb * (BN * 128), &map_b, bres_bar, kb * BK, nb * BN);
+            }
             int stage = 0;
             uint32_t phase = 0;
-            for (int mb = mb0; mb < m_blocks; mb += mb_step) {
+            for (int q = 0;; ++q) {
+                tq.publish(q, mb < m_blocks ? mb : -1);
+                if (mb >= m_blocks) break;
+                const int next = atomicAdd(&ctr[nb], 1);   // its latency hides behind the loads below
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), BM * BK * 2);
                     tma_load_2d(base + S::kRing + stage * (BM * BK * 2), &map_a, full_bar(stage), kb * BK, mb * BM);
                     if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
                 }
+                mb = next;
             }
         }
     } else if (warp == 1) {
@@ -361,8 +418,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t idesc = tc_idesc_f16(BM, BN);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            mbar_wait(bres_bar, 0);
-            for (int mb = mb0; mb < m_blocks; mb += mb_step) {
+            for (int q = 0; tq.take(q) >= 0; ++q) {
+                if (q == 0) mbar_wait(bres_bar, 0);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -389,7 +446,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         stage_bias<BN>(sbias, ep.bias, nb, N, lane);       // the column block never changes
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int mb = mb0; mb < m_blocks; mb += mb_step) {
+        for (int q = 0;; ++q) {
+            const int mb = tq.take(q);
+            if (mb < 0) break;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, set, lane, ep);
@@ -403,6 +462,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tc_dealloc(tmem_base, BN <= 128 ? 256 : 512);
+    if (threadIdx.x == 0) release_tile_counters(ctr, n_blocks);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -438,6 +498,44 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, 
     return 0;
 }
 
+// Pool of zero-initialised ticket counters (per device).  Eager launches take theirs round-robin from the first half
+// (a region is reused only ~100k launches later, long after its launch has reset it); launches recorded into a CUDA graph
+// take theirs from the second half and keep them for the life of the process, because a replay uses the same addresses
+// every time and must never share them with a concurrent eager launch.
+constexpr int POOL_INTS = 1 << 21;   // 8 MB
+struct CounterPool {
+    int* base = nullptr;
+    int eager = 0, pinned = POOL_INTS / 2;
+};
+static CounterPool g_pools[16];
+static std::mutex g_pool_mutex;
+
+int take_counters(int n, cudaStream_t stream, int** out) {
+    int dev = 0;
+    B200_CHECK_CUDA(cudaGetDevice(&dev));
+    B200_REQUIRE(dev >= 0 && dev < 16, "gemm_tc: device ordinal %d is not supported", dev);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    B200_CHECK_CUDA(cudaStreamIsCapturing(stream, &cap));
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    CounterPool& p = g_pools[dev];
+    if (p.base == nullptr) {
+        B200_REQUIRE(cap == cudaStreamCaptureStatusNone,
+                     "gemm_tc: the first GEMM on a device must not run inside a CUDA graph capture (run one warm-up step)");
+        B200_CHECK_CUDA(cudaMalloc(&p.base, sizeof(int) * POOL_INTS));
+        B200_CHECK_CUDA(cudaMemset(p.base, 0, sizeof(int) * POOL_INTS));
+    }
+    if (cap != cudaStreamCaptureStatusNone) {
+        B200_REQUIRE(p.pinned + n <= POOL_INTS, "gemm_tc: out of ticket counters for graph-captured launches");
+        *out = p.base + p.pinned;
+        p.pinned += n;
+    } else {
+        if (p.eager + n > POOL_INTS / 2) p.eager = 0;
+        *out = p.base + p.eager;
+        p.eager += n;
+    }
+    return 0;
+}
+
 template <int BN>
 int launch_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
               const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
@@ -454,7 +552,10 @@ int launch_tc(const __half* A, long long lda, const __half* B, __half* C, long l
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < sms ? tiles : sms;
-    kern<<<grid, THREADS, TcSmem<BN>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep);
+    int* ctr = nullptr;
+    rc = take_counters(2, stream, &ctr);
+    if (rc) return rc;
+    kern<<<grid, THREADS, TcSmem<BN>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep, ctr);
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -477,7 +578,10 @@ int launch_ws(const __half* A, long long lda, const __half* B, __half* C, long l
     int per_block = sms / n_blocks;            // CTAs bound to one column block
     if (per_block > m_blocks) per_block = m_blocks;
     if (per_block < 1) per_block = 1;
-    kern<<<per_block * n_blocks, THREADS, WsSmem<BN>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep);
+    int* ctr = nullptr;
+    rc = take_counters(n_blocks + 1, stream, &ctr);
+    if (rc) return rc;
+    kern<<<per_block * n_blocks, THREADS, WsSmem<BN>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep, ctr);
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

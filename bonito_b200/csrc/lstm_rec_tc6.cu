@@ -21,7 +21,8 @@
 //     produces it writes the layout [tile][T][rank][48 chunks][256 columns]); the MMA warp streams it into a 4-deep
 //     shared-memory ring per sub-tile with cp.async.bulk, three steps ahead: no global load, and no register prefetch
 //     buffers, in the epilogue warps.
-//   * per (step, sub-tile) one elected thread issues 2 x 24 tcgen05.mma (M=128, N=16, K=16); eight epilogue warps pull
+//   * per (step, sub-tile) one elected thread of that sub-tile's issuing warp issues 2 x 24 tcgen05.mma (M=128, N=16, K=16);
+//     eight epilogue warps pull
 //     the gate pre-activations with tcgen05.ld.16x256b (the mma-accumulator fragment: with rows ordered
 //     [8 units x (i,f,g,o)] one thread holds all four gates of a (unit, chunk)), add gx, update (c, h) in registers,
 //     stage the new h block in shared memory and write it to Y[t].
@@ -53,8 +54,8 @@ constexpr int CS = 6;
 constexpr int UPC = H / CS;        // 64 units per CTA
 constexpr int ROWS = 4 * UPC;      // 256 gate rows per CTA
 constexpr int EW = 8;              // epilogue warps per sub-tile (one 32-row block each)
-constexpr int MMA_WARP = NS * EW;  // warp 24: MMA issuer + gx producer + TMEM allocation
-constexpr int THREADS = (MMA_WARP + 1) * 32;      // 800
+constexpr int MMA_WARP = NS * EW;  // warps 24, 25, 26: MMA issuer + gx producer of sub-tile 0, 1, 2 (warp 24 also allocates TMEM)
+constexpr int THREADS = (MMA_WARP + NS) * 32;     // 864
 constexpr int GXD = 4;             // depth of the gx ring (steps)
 constexpr uint32_t HT = (H / 8) * SN * 16;        // one h tile: 48 k-chunks x 16 chunks x 16 B = 12288 B
 constexpr uint32_t GXS = SN * ROWS * 2;           // gx of one (step, sub-tile) for this CTA: 8192 B
@@ -293,28 +294,29 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
     tc_fence_after();
     cluster_sync_all();  // every CTA's barriers are initialised before any peer's bulk copy can land
 
-    if (warp == MMA_WARP) {
-        // ===== MMA issuer + gx producer: the whole warp walks the (step, sub-tile) items, one elected lane issues =====
+    if (warp >= MMA_WARP) {
+        // ===== MMA issuer + gx producer of ONE sub-tile: the whole warp walks the steps, one elected lane issues =====
+        // One issuing warp per sub-tile, each on its own SM sub-partition: a single warp serving the three sub-tiles in
+        // turn waited for the h tile of sub-tile 1 while that of sub-tile 2 was already complete, and its ~1500 issue
+        // cycles per step all fell on the sub-partition it shares with six epilogue warps.
+        const int sub = warp - MMA_WARP;
         constexpr uint32_t idesc = tc_idesc_f16(128, SN);
-        const __half* gx_cta = gx + (size_t)rank * (NB * ROWS);
-        auto load_gx = [&](int step, int sub) {     // gx of (step, sub) -> ring slot step % GXD
+        const __half* gx_cta = gx + (size_t)rank * (NB * ROWS) + (size_t)sub * (SN * ROWS);
+        auto load_gx = [&](int step) {     // gx of (step, sub) -> ring slot step % GXD
             const int t = reverse ? (T - 1 - step) : step;
             const int slot = step & (GXD - 1);
             const uint32_t bar = bars.gxfull(sub, slot);
             mbar_expect_tx(bar, GXS);
-            bulk_load_global(base + OFF_GX + (uint32_t)(sub * GXD + slot) * GXS,
-                             gx_cta + (size_t)t * (CS * NB * ROWS) + (size_t)sub * (SN * ROWS), GXS, bar);
+            bulk_load_global(base + OFF_GX + (uint32_t)(sub * GXD + slot) * GXS, gx_cta + (size_t)t * (CS * NB * ROWS), GXS, bar);
         };
-        if (elect_one_sync()) {
-            for (int s = 0; s < GXD - 1 && s < T; ++s)
-                for (int sub = 0; sub < nsub; ++sub) load_gx(s, sub);
-        }
-        __syncwarp();
-        for (int step = 0; step < T; ++step) {
-            const int p = step & 1;
-#pragma unroll
-            for (int sub = 0; sub < NS; ++sub) {
-                if (sub >= nsub) break;
+        if (sub < nsub) {
+            if (elect_one_sync()) {
+                for (int s = 0; s < GXD - 1 && s < T; ++s) load_gx(s);
+            }
+            __syncwarp();
+            const uint32_t d1 = tmem_base + COL_D + sub * 32, d2 = d1 + 16;
+            for (int step = 0; step < T; ++step) {
+                const int p = step & 1;
                 const uint32_t hbar = bars.hfull(sub, p);
                 if (VARIANT == 3 && sub == 0 && blockIdx.x == 0 && lane == 0) g_timeline6[step % TL_STEPS][7] = clock64();
                 if (step > 0) mbar_wait(hbar, (uint32_t)((((step + 1) >> 1) - 1) & 1));
@@ -332,7 +334,6 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
                     tc_fence_after();
                     // B tile: [k-chunk][16 rows][16 B]; one K=16 step = two k-chunks = 512 B
                     const uint64_t bdesc0 = tc_smem_desc_noswz(base + OFF_H + (uint32_t)(sub * 2 + p) * HT, SN * 16, 128);
-                    const uint32_t d1 = tmem_base + COL_D + sub * 32, d2 = d1 + 16;
 #pragma unroll
                     for (int ks = 0; ks < H / 16; ++ks) {
                         const uint32_t acol = (uint32_t)ks * 8;
@@ -343,7 +344,7 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
                     }
                     tc_commit(bars.dfull(sub));
                     if (VARIANT == 3 && sub == 0 && blockIdx.x == 0) g_timeline6[step % TL_STEPS][1] = clock64();
-                    if (step + GXD - 1 < T) load_gx(step + GXD - 1, sub);   // into the slot of step-1 (consumed, see above)
+                    if (step + GXD - 1 < T) load_gx(step + GXD - 1);   // into the slot of step-1 (consumed, see above)
                 }
                 __syncwarp();
             }
