@@ -71,15 +71,15 @@ int b200_gemm_fwd(const void* a, long long lda, const void* b, const void* bias,
                   int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
                   long long stride_inner, long long stride_outer, int impl, void* stream) {
     return b200_gemm_fwd_ex(a, lda, b, bias, c, ldc, m, n, k, act, lo, hi, rows_inner, valid_inner, stride_inner,
-                            stride_outer, 0, 0, impl, 0, stream);
+                            stride_outer, 0, 0, 0, 0, impl, 0, stream);
 }
 
 int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bias, void* c, long long ldc, int m,
                      int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
-                     long long stride_inner, long long stride_outer, int cb_width, int cb_rows, int impl, int max_ctas,
-                     void* stream) {
+                     long long stride_inner, long long stride_outer, int group, long long stride_group, int cb_width,
+                     int cb_rows, int impl, int max_ctas, void* stream) {
     B200_REQUIRE(a && b && c, "gemm: null pointer argument");
-    B200_REQUIRE(m >= 0 && n > 0 && k > 0 && rows_inner > 0, "gemm: bad sizes m=%d n=%d k=%d", m, n, k);
+    B200_REQUIRE(m >= 0 && n > 0 && k > 0 && rows_inner > 0 && group >= 0, "gemm: bad sizes m=%d n=%d k=%d", m, n, k);
     B200_REQUIRE(k % 8 == 0 && lda % 8 == 0 && n % 8 == 0 && ldc % 8 == 0,
                  "gemm: k, lda, n, ldc must be multiples of 8 (k=%d lda=%lld n=%d ldc=%lld)", k, lda, n, ldc);
     B200_REQUIRE(cb_width >= 0 && cb_rows >= 0 && cb_width % 32 == 0 && (cb_width == 0 || act != B200_ACT_SWIGLU),
@@ -98,6 +98,8 @@ int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bi
     ep.map.valid_inner = valid_inner;
     ep.map.stride_inner = stride_inner;
     ep.map.stride_outer = stride_outer;
+    ep.map.group = group;
+    ep.map.stride_group = stride_group;
     ep.cb_width = cb_width;
     ep.cb_rows = cb_rows;
     if (impl == B200_GEMM_AUTO) {

@@ -105,19 +105,29 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 }
 
 // Row remap applied by GEMM epilogues: input row r -> (outer, inner) = divmod(r, rows_inner);
-// rows with inner >= valid_inner are dropped; output row = inner*stride_inner + outer*stride_outer.
+// rows with inner >= valid_inner are dropped; output row = inner*stride_inner + outer*stride_outer, or, with a second
+// level (group > 0): (outer2, outer1) = divmod(outer, group), output row = inner*stride_inner + outer1*stride_outer +
+// outer2*stride_group  (chunk -> (tile, chunk in tile) or (tile, frame) splits of the tile layout).
 struct RowMap {
     int rows_inner;
     int valid_inner;
     long long stride_inner;
     long long stride_outer;
+    int group;
+    long long stride_group;
 };
 
 __device__ __forceinline__ long long map_row(const RowMap& m, int r) {
     int outer = r / m.rows_inner;
     int inner = r - outer * m.rows_inner;
     if (inner >= m.valid_inner) return -1;
-    return (long long)inner * m.stride_inner + (long long)outer * m.stride_outer;
+    long long o = (long long)inner * m.stride_inner;
+    if (m.group > 0) {
+        const int outer2 = outer / m.group;
+        o += (long long)outer2 * m.stride_group;
+        outer -= outer2 * m.group;
+    }
+    return o + (long long)outer * m.stride_outer;
 }
 
 struct GemmEpilogue {

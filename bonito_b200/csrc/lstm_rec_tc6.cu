@@ -21,7 +21,10 @@
 //     produces it writes the layout [tile][T][rank][48 chunks][256 columns]); the MMA warp streams it into a 4-deep
 //     shared-memory ring per sub-tile with cp.async.bulk, three steps ahead: no global load, and no register prefetch
 //     buffers, in the epilogue warps.
-//   * per (step, sub-tile) one elected thread of that sub-tile's issuing warp issues 2 x 24 tcgen05.mma (M=128, N=16, K=16);
+//   * per (step, sub-tile) one elected thread issues 2 x 24 tcgen05.mma (M=128, N=16, K=16) -- ONE issuing warp serves the
+//     three sub-tiles in turn: giving each sub-tile its own issuing warp was measured slower (3474 vs 3089 cycles per
+//     step), because the in-order issue is what keeps the three sub-tiles staggered: with three issuers they phase-lock,
+//     their MMAs interleave in the tensor pipe and all 24 epilogue warps then run their cell updates at the same time;
 //     eight epilogue warps pull
 //     the gate pre-activations with tcgen05.ld.16x256b (the mma-accumulator fragment: with rows ordered
 //     [8 units x (i,f,g,o)] one thread holds all four gates of a (unit, chunk)), add gx, update (c, h) in registers,
@@ -54,8 +57,8 @@ constexpr int CS = 6;
 constexpr int UPC = H / CS;        // 64 units per CTA
 constexpr int ROWS = 4 * UPC;      // 256 gate rows per CTA
 constexpr int EW = 8;              // epilogue warps per sub-tile (one 32-row block each)
-constexpr int MMA_WARP = NS * EW;  // warps 24, 25, 26: MMA issuer + gx producer of sub-tile 0, 1, 2 (warp 24 also allocates TMEM)
-constexpr int THREADS = (MMA_WARP + NS) * 32;     // 864
+constexpr int MMA_WARP = NS * EW;  // warp 24: MMA issuer + gx producer + TMEM allocation
+constexpr int THREADS = (MMA_WARP + 1) * 32;      // 800
 constexpr int GXD = 4;             // depth of the gx ring (steps)
 constexpr uint32_t HT = (H / 8) * SN * 16;        // one h tile: 48 k-chunks x 16 chunks x 16 B = 12288 B
 constexpr uint32_t GXS = SN * ROWS * 2;           // gx of one (step, sub-tile) for this CTA: 8192 B
@@ -126,7 +129,7 @@ struct Bars {
 template <int VARIANT, int EXCH>
 __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned char* __restrict__ hx, int T, int nb,
                                               int reverse, uint32_t rank, int sub, int ew, uint32_t tmem_base,
-                                              uint32_t base, unsigned char* gbase, Bars bars, int lane) {
+                                              uint32_t base, unsigned char* gbase, Bars bars, int lane, int ablate) {
     const int r = lane >> 2, q = lane & 3;
     const int quarter = ew & 3, which = ew >> 2, blk = which * 4 + quarter;
     const int u0 = (int)rank * UPC + blk * 8;                                   // first unit of this block
@@ -153,7 +156,7 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned c
         const uint32_t stage_off = OFF_STAGE + (uint32_t)((p * NS + sub) * EW + ew) * STAGE_WARP;
         __half* stage = reinterpret_cast<__half*>(gbase + stage_off);
         // input projection of this step from the ring (landed ~3 steps ago: never on the recurrence's critical path)
-        mbar_wait(bars.gxfull(sub, slot), (uint32_t)((step / GXD) & 1));
+        if (!(ablate & 1)) mbar_wait(bars.gxfull(sub, slot), (uint32_t)((step / GXD) & 1));
         uint2 g[2][2];
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -180,11 +183,17 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned c
                 const float af = __uint_as_float(a[4 * j + 2 + e]) + __high2float(g01);
                 const float ag = __uint_as_float(b[4 * j + e]) + __low2float(g23);
                 const float ao = __uint_as_float(b[4 * j + 2 + e]) + __high2float(g23);
-                float si, sf, tg, so;
-                gate_activations(ai, af, ag, ao, si, sf, tg, so);
-                const float c = fmaf(sf, c_state[j][e], si * tg);
+                float si, sf, tg, so, c, hval;
+                if (ablate & 4) {      // timing experiment: no SFU work (wrong results)
+                    c = 0.25f * (af + ai + ag) + 0.5f * c_state[j][e];
+                    hval = 0.1f * (ao + c);
+                } else {
+                    gate_activations(ai, af, ag, ao, si, sf, tg, so);
+                    c = fmaf(sf, c_state[j][e], si * tg);
+                    hval = so * tanh_f(c);
+                }
                 c_state[j][e] = c;
-                stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(so * tanh_f(c));
+                stage[(8 * j + 2 * q + e) * 8 + r] = __float2half_rn(hval);
             }
         if (EXCH == 0) {
             fence_proxy_async_smem();   // staged block (generic stores) -> visible to the bulk-copy engine
@@ -217,7 +226,7 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned c
                     bulk_multicast(base + OFF_H + (uint32_t)(sub * 2 + (p ^ 1)) * HT + dst_off, g, STAGE_WARP,
                                    bars.hfull(sub, p ^ 1), (uint16_t)((1u << CS) - 1u));
             }
-            if (y_ok) *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;   // -> Y[t], off the critical path
+            if (y_ok && !(ablate & 2)) *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;   // -> Y[t], off the critical path
         }
         if (tl && ew == 0) g_timeline6[ts][5] = clock64();
         __syncwarp();
@@ -234,7 +243,7 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned c
 template <int VARIANT, int EXCH>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(THREADS, 1)
 lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ whh, __half* __restrict__ y,
-                    unsigned char* __restrict__ hx, int T, int N, int reverse) {
+                    unsigned char* __restrict__ hx, int T, int N, int reverse, int ablate) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -294,29 +303,28 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
     tc_fence_after();
     cluster_sync_all();  // every CTA's barriers are initialised before any peer's bulk copy can land
 
-    if (warp >= MMA_WARP) {
-        // ===== MMA issuer + gx producer of ONE sub-tile: the whole warp walks the steps, one elected lane issues =====
-        // One issuing warp per sub-tile, each on its own SM sub-partition: a single warp serving the three sub-tiles in
-        // turn waited for the h tile of sub-tile 1 while that of sub-tile 2 was already complete, and its ~1500 issue
-        // cycles per step all fell on the sub-partition it shares with six epilogue warps.
-        const int sub = warp - MMA_WARP;
+    if (warp == MMA_WARP) {
+        // ===== MMA issuer + gx producer: the whole warp walks the (step, sub-tile) items, one elected lane issues =====
         constexpr uint32_t idesc = tc_idesc_f16(128, SN);
-        const __half* gx_cta = gx + (size_t)rank * (NB * ROWS) + (size_t)sub * (SN * ROWS);
-        auto load_gx = [&](int step) {     // gx of (step, sub) -> ring slot step % GXD
+        const __half* gx_cta = gx + (size_t)rank * (NB * ROWS);
+        auto load_gx = [&](int step, int sub) {     // gx of (step, sub) -> ring slot step % GXD
             const int t = reverse ? (T - 1 - step) : step;
             const int slot = step & (GXD - 1);
             const uint32_t bar = bars.gxfull(sub, slot);
             mbar_expect_tx(bar, GXS);
-            bulk_load_global(base + OFF_GX + (uint32_t)(sub * GXD + slot) * GXS, gx_cta + (size_t)t * (CS * NB * ROWS), GXS, bar);
+            bulk_load_global(base + OFF_GX + (uint32_t)(sub * GXD + slot) * GXS,
+                             gx_cta + (size_t)t * (CS * NB * ROWS) + (size_t)sub * (SN * ROWS), GXS, bar);
         };
-        if (sub < nsub) {
-            if (elect_one_sync()) {
-                for (int s = 0; s < GXD - 1 && s < T; ++s) load_gx(s);
-            }
-            __syncwarp();
-            const uint32_t d1 = tmem_base + COL_D + sub * 32, d2 = d1 + 16;
-            for (int step = 0; step < T; ++step) {
-                const int p = step & 1;
+        if (elect_one_sync()) {
+            for (int s = 0; s < GXD - 1 && s < T && !(ablate & 1); ++s)
+                for (int sub = 0; sub < nsub; ++sub) load_gx(s, sub);
+        }
+        __syncwarp();
+        for (int step = 0; step < T; ++step) {
+            const int p = step & 1;
+#pragma unroll
+            for (int sub = 0; sub < NS; ++sub) {
+                if (sub >= nsub) break;
                 const uint32_t hbar = bars.hfull(sub, p);
                 if (VARIANT == 3 && sub == 0 && blockIdx.x == 0 && lane == 0) g_timeline6[step % TL_STEPS][7] = clock64();
                 if (step > 0) mbar_wait(hbar, (uint32_t)((((step + 1) >> 1) - 1) & 1));
@@ -334,6 +342,7 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
                     tc_fence_after();
                     // B tile: [k-chunk][16 rows][16 B]; one K=16 step = two k-chunks = 512 B
                     const uint64_t bdesc0 = tc_smem_desc_noswz(base + OFF_H + (uint32_t)(sub * 2 + p) * HT, SN * 16, 128);
+                    const uint32_t d1 = tmem_base + COL_D + sub * 32, d2 = d1 + 16;
 #pragma unroll
                     for (int ks = 0; ks < H / 16; ++ks) {
                         const uint32_t acol = (uint32_t)ks * 8;
@@ -344,7 +353,7 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
                     }
                     tc_commit(bars.dfull(sub));
                     if (VARIANT == 3 && sub == 0 && blockIdx.x == 0) g_timeline6[step % TL_STEPS][1] = clock64();
-                    if (step + GXD - 1 < T) load_gx(step + GXD - 1);   // into the slot of step-1 (consumed, see above)
+                    if (step + GXD - 1 < T && !(ablate & 1)) load_gx(step + GXD - 1, sub);   // into the slot of step-1 (consumed, see above)
                 }
                 __syncwarp();
             }
@@ -352,7 +361,7 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
     } else {
         const int sub = warp / EW, ew = warp % EW;
         if (sub < nsub)
-            epilogue_warp<VARIANT, EXCH>(y, hx, T, nb, reverse, rank, sub, ew, tmem_base, base, gbase, bars, lane);
+            epilogue_warp<VARIANT, EXCH>(y, hx, T, nb, reverse, rank, sub, ew, tmem_base, base, gbase, bars, lane, ablate);
     }
 
     tc_fence_before();
@@ -382,12 +391,15 @@ int launch_lstm_rec_tc6(const __half* gx, const __half* whh, __half* y, void* wo
     // default: multicast bulk copies out of the L2 staging buffer; "dsmem": peer-to-peer bulk copies (cross-check)
     const char* ex = getenv("B200_LSTM_EXCH");
     const bool dsmem = ex && ex[0] == 'd';
+    // B200_LSTM_ABLATE (timing experiments, wrong results): 1 = no gx traffic, 2 = no Y stores, 4 = no SFU work in the cell update
+    const char* ab = getenv("B200_LSTM_ABLATE");
+    const int ablate = ab ? atoi(ab) : 0;
 #define LAUNCH6(v, e)                                                                                                   \
     do {                                                                                                                \
         B200_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_tc6_kernel<v, e>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                              (int)SMEM_BYTES));                                                         \
         lstm_rec_tc6_kernel<v, e><<<tiles * CS, THREADS, SMEM_BYTES, stream>>>(gx, whh, y, (unsigned char*)workspace, T, \
-                                                                               N, reverse);                             \
+                                                                               N, reverse, ablate);                     \
     } while (0)
     if (variant == 3 && dsmem) LAUNCH6(3, 0);
     else if (variant == 3) LAUNCH6(3, 1);

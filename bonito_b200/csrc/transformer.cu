@@ -9,6 +9,8 @@
 //   swiglu          flash_attn/ops/activations.py:107-111  float(gate) * float(y) / (1 + exp(-gate)), rounded once
 // First correct versions: attention runs on the legacy mma.sync path (it is ~6 % of the layer's FLOPs because of the
 // 256-wide window); the GEMMs, 94 % of the work, are the tcgen05 kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -381,13 +383,23 @@ int launch_swiglu(const __half* h, __half* out, long long M, int F, cudaStream_t
     return 0;
 }
 
+bool attention_tc_supported(int head_dim, int wl, int wr);
+int launch_attention_tc(const __half* qkv, __half* out, int N, int T, int NH, int wl, int wr, cudaStream_t stream);
+
 int launch_attention(__half* qkv, const __half* cos_sin, __half* out, int N, int T, int NH, int head_dim, int wl,
                      int wr, cudaStream_t stream) {
     B200_REQUIRE(head_dim == HD, "attention: head_dim %d is not supported (64)", head_dim);
-    if (wl < 0) wl = T;
-    if (wr < 0) wr = T;
     const long long tokens = (long long)N * T, work = tokens * 2 * NH * 4;
     rotary_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(qkv, cos_sin, tokens, T, NH);
+    // product path: tcgen05 kernel (attention_tc.cu) for windows of at most 128 keys each way (sup v5: 127 / 128);
+    // B200_ATTN_IMPL=mma keeps the mma.sync kernel below as an on-device cross-check, and it serves every other window
+    const char* impl = getenv("B200_ATTN_IMPL");
+    if (!(impl && impl[0] == 'm') && attention_tc_supported(head_dim, wl, wr)) {
+        B200_CHECK_CUDA(cudaGetLastError());
+        return launch_attention_tc(qkv, out, N, T, NH, wl, wr, stream);
+    }
+    if (wl < 0) wl = T;
+    if (wr < 0) wr = T;
     dim3 grid((T + AQ - 1) / AQ, NH, N);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
     attention_kernel<<<grid, 128, 0, stream>>>(qkv, nullptr, out, T, NH, wl, wr, scale_log2e);

@@ -443,8 +443,11 @@ class LstmCrfPlan:
         cur, nxt = b["ya"], b["yb"]
 
         if not streams:
-            for i in range(nt):
-                conv_gemm(i, main)
+            # all tiles in one launch: chunk n of the stem -> (tile n / TB, row n % TB); rows r = n*Tp + t
+            with staged("conv_gemm", main):
+                native.gemm(b["stem"], self.s3 * self.c2, self.w3, self.b3, b["ya"], H, N * Tp, H, self.k3 * self.c2,
+                            act=self.act3, rows_inner=Tp, valid_inner=T, stride_inner=TB, stride_outer=1, group=TB,
+                            stride_group=T * TB, impl=gemm_impl, stream=main)
             if return_features:
                 feats["conv"] = gather(cur)
             for li, layer in enumerate(self.lstm):
@@ -453,8 +456,21 @@ class LstmCrfPlan:
                 cur, nxt = nxt, cur
                 if return_features:
                     feats[f"lstm{li}"] = gather(cur)
-            for i in range(nt):
-                crf_gemm(cur, i, main)
+            # all tiles in one launch: rows r = (tile*T + t)*TB + i -> out[tile*TB + i][t]; rows of chunks beyond the batch
+            # (last tile) land behind the N valid chunks and are cut off by `valid_rows`
+            if N % TB == 0:
+                with staged("crf_gemm", main):
+                    native.gemm(cur, H, self.wl, self.bl, out, self.n_scores, nt * T * TB, self.n_scores, H, act=self.act_l,
+                                lo=self.lo, hi=self.hi, rows_inner=TB, valid_inner=TB, stride_inner=T, stride_outer=1,
+                                group=T, stride_group=TB * T, impl=gemm_impl, stream=main)
+            else:
+                full = N // TB
+                if full:
+                    with staged("crf_gemm", main):
+                        native.gemm(cur, H, self.wl, self.bl, out, self.n_scores, full * T * TB, self.n_scores, H,
+                                    act=self.act_l, lo=self.lo, hi=self.hi, rows_inner=TB, valid_inner=TB, stride_inner=T,
+                                    stride_outer=1, group=T, stride_group=TB * T, impl=gemm_impl, stream=main)
+                crf_gemm(cur, nt - 1, main)
             return (out, feats) if return_features else out
 
         b["start"].record(main)
@@ -496,7 +512,10 @@ class LstmCrfPlan:
         import os
         if self.tile and os.environ.get("B200_LSTM_TILE", "1") != "0":
             if tiled is None:
-                tiled = (not return_features) and x.shape[0] > self.tile and os.environ.get("B200_TILE_STREAMS", "1") != "0"
+                # Default: the layer-by-layer schedule (14 launches per batch).  With two batches in flight on two streams
+                # (score_batches, bench.py) it measured faster than per-tile streams (17.8 vs 18.8 ms per 512-chunk batch):
+                # the GEMMs / decode of one batch fill the 82 SMs the other batch's recurrent clusters leave free.
+                tiled = (not return_features) and x.shape[0] > self.tile and os.environ.get("B200_TILE_STREAMS", "0") != "0"
             return self.forward_tiles(x, out=out, gemm_impl=gemm_impl, events=events, return_features=return_features,
                                       streams=tiled, slot=slot)
         if slot != 0:

@@ -27,8 +27,8 @@ SIGNATURES = {
     "b200_gemm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                               c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_void_p]),
     "b200_gemm_fwd_ex": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
-                                 c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_int, c_int,
-                                 c_void_p]),
+                                 c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_longlong, c_int, c_int,
+                                 c_int, c_int, c_void_p]),
     "b200_conv_first_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                     c_int, c_void_p]),
     "b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -126,7 +126,7 @@ def conv_stem(x, w1, b1, act1, w2, b2, act2, out, lp, padl):
 
 def gemm(a_ptr_tensor, lda, b, bias, c, ldc, m, n, k, act=ACT_NONE, lo=0.0, hi=0.0,
          rows_inner=None, valid_inner=None, stride_inner=1, stride_outer=0, impl=GEMM_AUTO, stream=None, max_ctas=0,
-         cb_width=0, cb_rows=0):
+         cb_width=0, cb_rows=0, group=0, stride_group=0):
     """C = act(A B^T + bias); `a_ptr_tensor` / `c` only supply base pointers (rows may overlap / be remapped; `cb_*`:
     column blocks, see b200_gemm_fwd_ex)."""
     lib = require()
@@ -135,7 +135,8 @@ def gemm(a_ptr_tensor, lda, b, bias, c, ldc, m, n, k, act=ACT_NONE, lo=0.0, hi=0
     with torch.cuda.device(c.device):
         rc = lib.b200_gemm_fwd_ex(_ptr(a_ptr_tensor), lda, _ptr(_f16(b, "b")), _ptr(bias), _ptr(c), ldc, m, n, k,
                                   act, float(lo), float(hi), rows_inner, valid_inner, stride_inner, stride_outer,
-                                  int(cb_width), int(cb_rows), impl, int(max_ctas), _stream(stream))
+                                  int(group), int(stride_group), int(cb_width), int(cb_rows), impl, int(max_ctas),
+                                  _stream(stream))
     _check(rc, "b200_gemm_fwd")
     return c
 

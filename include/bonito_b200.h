@@ -77,14 +77,16 @@ int b200_gemm_fwd(const void* a, long long lda, const void* b, const void* bias,
  * Same, with
  *   max_ctas  a cap on the number of (persistent) CTAs the tcgen05 kernel may occupy (0 = every SM): the tile-pipelined
  *             engine caps the GEMMs it runs next to resident recurrent clusters;
+ *   group, stride_group  second level of the row map (group = 0: off): (outer2, outer1) = divmod(outer, group),
+ *             out_row = inner*stride_inner + outer1*stride_outer + outer2*stride_group -- e.g. chunk n -> (tile n/48, n%48);
  *   cb_width, cb_rows  column blocks (cb_width = 0: off; multiple of 32): output column c of mapped row R is written to
  *             row R + (c / cb_width) * cb_rows, column c % cb_width.  With ldc = cb_width this lays the LSTM input
  *             projection out as [t][cluster rank][chunk][cb_width], one contiguous block per recurrent CTA and step.
  */
 int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bias, void* c, long long ldc, int m,
                      int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
-                     long long stride_inner, long long stride_outer, int cb_width, int cb_rows, int impl, int max_ctas,
-                     void* stream);
+                     long long stride_inner, long long stride_outer, int group, long long stride_group, int cb_width,
+                     int cb_rows, int impl, int max_ctas, void* stream);
 
 /*
  * Cluster size the packed LSTM operands must be laid out for (0: hidden size unsupported).
