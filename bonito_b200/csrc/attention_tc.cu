@@ -2,22 +2,24 @@
 // Reference semantics: bonito/transformer/model.py:42-79 -- flash_attn_qkvpacked_func(window_size=(wl, wr)), non-causal,
 // softmax scale 1/sqrt(head_dim); the rotary embedding has been applied to q and k in place before (rotary_kernel).
 //
-// One CTA per (chunk, head, 128-query tile).  With wl, wr <= 128 the queries of a tile see at most three 128-key tiles
-// (the one before, its own, the one after), so the whole band of scores fits in tensor memory at once:
-//   * TMA (3-D tensor map over qkv [N][T][3*heads*64], SWIZZLE_128B, out-of-range rows zero-filled) brings Q [128 x 64],
-//     K_j [128 x 64] and V_j [128 keys x 64] (j = 0..2) into shared memory;
+// Persistent kernel, one CTA per SM; a work item is one (chunk, head): the CTA walks its 128-query tiles in order.  With
+// wl, wr <= 128 the queries of tile qt see at most the three 128-key tiles qt-1, qt, qt+1, so
+//   * K and V tiles travel through 4-slot shared-memory rings (TMA, 3-D tensor map over qkv [N][T][3*heads*64],
+//     SWIZZLE_128B, out-of-range rows zero-filled): every key tile is loaded ONCE per (chunk, head) and used by three
+//     query tiles; the tile needed next is always in flight while the current one is processed; Q is double buffered;
 //   * S_j = Q K_j^T: 4 tcgen05.mma (M=128, N=128, K=16) per key tile, fp32 accumulators in TMEM columns [128j, 128j+128);
 //   * four softmax warps, one thread per query row (tcgen05.ld 32x32b: thread i of warp w owns TMEM lane 32w+i): each key
 //     tile is normalised on its OWN row maximum m_j -- the 128 scores of a row and tile live in registers between the
 //     maximum and the exponentials, so S is read from TMEM exactly once -- and P_j = 2^((s - m_j) * scale) is written back
-//     as fp16 pairs into the first 64 columns of S_j (tcgen05.st), i.e. as a TMEM-resident A operand;
+//     as fp16 pairs into the first 64 columns of S_j (tcgen05.st), i.e. as a TMEM-resident A operand.  32-column pieces
+//     that a whole warp sees unmasked take a compare-free path; pieces masked for the whole warp are not even read;
 //   * O_j = P_j V_j: 8 tcgen05.mma (M=128, N=64, K=16) per key tile with A from TMEM and B = V_j straight from its TMA
 //     layout (rows = keys = K, 128-byte rows of 64 head dims: the MN-major SWIZZLE_128B operand, "transpose B" bit of the
 //     instruction descriptor), accumulated into the LAST 64 columns of S_j; PV_j runs while the softmax warps work on j+1;
 //   * epilogue: O = sum_j O_j 2^((m_j - M) scale) / sum_j l_j 2^((m_j - M) scale), M = max_j m_j -- three independent
 //     partial softmaxes combined per row, no running-maximum rescaling of accumulators in flight.
-// Masked scores (outside the window or outside the chunk) get P = 0; 32-column pieces that are masked for a whole warp are
-// neither read nor exponentiated.
+// (First version: one CTA per query tile, nothing prefetched: 41 ms per sup step against 36 ms for the mma.sync kernel --
+// every CTA paid the full load latency and a TMEM allocation for 128 queries.)
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -25,11 +27,11 @@
 
 namespace {
 
-constexpr int BQ = 128, BKV = 128, HD = 64, NKT = 3;
+constexpr int BQ = 128, BKV = 128, HD = 64, NKT = 3, RING = 4;
 constexpr int THREADS = 160;                       // 4 softmax warps + 1 TMA / MMA warp
 constexpr uint32_t TILE_BYTES = BQ * HD * 2;       // 16 KB: one 128 x 64 fp16 tile (128-byte rows)
-constexpr uint32_t OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = OFF_K + NKT * TILE_BYTES, OFF_BARS = OFF_V + NKT * TILE_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_BARS + 128 + 1024;
+constexpr uint32_t OFF_Q = 0, OFF_K = 2 * TILE_BYTES, OFF_V = OFF_K + RING * TILE_BYTES, OFF_BARS = OFF_V + RING * TILE_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_BARS + 256 + 1024;   // ~162 KB
 constexpr uint32_t TMEM_COLS = 512;                // S_j | P_j | O_j share columns [128j, 128j+128), j < 3
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -39,168 +41,256 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+struct AttnBars {
+    uint32_t base;
+    __device__ __forceinline__ uint32_t qfull(int b) const { return base + 8u * (uint32_t)b; }              // 2
+    __device__ __forceinline__ uint32_t kvfull(int slot) const { return base + 16u + 8u * (uint32_t)slot; }   // RING (K and V of a key tile)
+    __device__ __forceinline__ uint32_t s(int j) const { return base + 48u + 8u * (uint32_t)j; }              // 3
+    __device__ __forceinline__ uint32_t p(int j) const { return base + 72u + 8u * (uint32_t)j; }              // 3
+    __device__ __forceinline__ uint32_t o() const { return base + 96u; }
+    __device__ __forceinline__ uint32_t tfree() const { return base + 104u; }
+};
+
 __global__ void __launch_bounds__(THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restrict__ out, int T, int NH, int wl, int wr,
-                    float scale_log2e) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restrict__ out, int N, int T, int NH, int wl,
+                    int wr, float scale_log2e) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-B alignment
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bars = base + OFF_BARS;
-    const uint32_t bar_qk = bars, bar_v = bars + 8, bar_o = bars + 16;
-    auto bar_s = [&](int j) { return bars + 24u + 8u * (uint32_t)j; };
-    auto bar_p = [&](int j) { return bars + 48u + 8u * (uint32_t)j; };
-    const uint32_t tmem_slot = bars + 72;
+    AttnBars bars;
+    bars.base = base + OFF_BARS;
+    const uint32_t tmem_slot = bars.base + 112;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q0 = blockIdx.x * BQ, h = blockIdx.y, n = blockIdx.z;
-    const int k0 = q0 - BKV;                       // first key of key tile 0
+    const int nqt = (T + BQ - 1) / BQ;             // query tiles per (chunk, head); key tiles -1 .. nqt are loaded
+    const int items = N * NH;
 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_qkv));
-        mbar_init(bar_qk, 1);
-        mbar_init(bar_v, 1);
-        mbar_init(bar_o, 1);
+        for (int b = 0; b < 2; ++b) mbar_init(bars.qfull(b), 1);
+        for (int sl = 0; sl < RING; ++sl) mbar_init(bars.kvfull(sl), 1);
         for (int j = 0; j < NKT; ++j) {
-            mbar_init(bar_s(j), 1);
-            mbar_init(bar_p(j), 4);                // one arrive per softmax warp
+            mbar_init(bars.s(j), 1);
+            mbar_init(bars.p(j), 4);               // one arrive per softmax warp
         }
+        mbar_init(bars.o(), 1);
+        mbar_init(bars.tfree(), 4);
         mbar_fence_init();
     }
     if (warp == 4) tc_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 72);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 112);
 
     if (warp == 4) {
-        // ===== TMA producer + MMA issuer =====
+        // ===== TMA producer + MMA issuer (one thread) =====
         if (elect_one_sync()) {
-            const int cq = h * HD, ck = NH * HD + h * HD, cv = 2 * NH * HD + h * HD;
-            mbar_expect_tx(bar_qk, (1 + NKT) * TILE_BYTES);
-            tma_load_3d(base + OFF_Q, &map_qkv, bar_qk, cq, q0, n);
-            for (int j = 0; j < NKT; ++j) tma_load_3d(base + OFF_K + j * TILE_BYTES, &map_qkv, bar_qk, ck, k0 + j * BKV, n);
-            mbar_expect_tx(bar_v, NKT * TILE_BYTES);
-            for (int j = 0; j < NKT; ++j) tma_load_3d(base + OFF_V + j * TILE_BYTES, &map_qkv, bar_v, cv, k0 + j * BKV, n);
-
-            // S_j = Q K_j^T  (both operands K-major, 128-byte swizzled rows of 64 head dims)
-            mbar_wait(bar_qk, 0);
-            tc_fence_after();
             constexpr uint32_t idesc_s = tc_idesc_f16(BQ, BKV);
-            const uint64_t qdesc = tc_smem_desc_sw128(base + OFF_Q);
-#pragma unroll
-            for (int j = 0; j < NKT; ++j) {
-                const uint64_t kdesc = tc_smem_desc_sw128(base + OFF_K + j * TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    tc_mma_ss(tmem_base + (uint32_t)(j * 128), qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-                tc_commit(bar_s(j));
-            }
-            // O_j = P_j V_j  (A = P_j from TMEM: lane = query, column c = keys 2c, 2c+1; B = V_j MN-major: K = keys are the
-            // 128-byte rows, 8 keys per 1024-byte swizzle atom, so one K = 16 step advances the descriptor by 2048 bytes)
-            mbar_wait(bar_v, 0);
             constexpr uint32_t idesc_o = tc_idesc_f16(BQ, HD) | (1u << 16);   // bit 16: B is MN-major
+            // Flat streams over all work items of this CTA: query tiles `it` (Q buffer it & 1) and key-tile loads `kl`
+            // (ring slot kl & 3).  Item i contributes nqt query tiles and nqt + 2 key tiles (kt = -1 .. nqt); query tile
+            // qt of the item uses the key-tile loads first_kl + qt, +1, +2.
+            int it = 0;                    // query tiles processed
+            int kl_issued = 0;             // key tiles whose loads have been issued
+            int q_issued = 0;              // query tiles whose Q load has been issued
+            int kl_released = 0;           // key tiles no query tile will read again (their ring slots may be refilled)
+            const int my_items = blockIdx.x < items ? (items - blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            const int total_q = my_items * nqt, total_k = my_items * (nqt + 2);
+
+            auto issue_loads = [&]() {
+                // key tiles: up to RING in flight beyond the released ones
+                while (kl_issued < total_k && kl_issued < kl_released + RING) {
+                    const int li = kl_issued / (nqt + 2), kt = kl_issued % (nqt + 2) - 1;
+                    const int item = blockIdx.x + li * (int)gridDim.x, n = item / NH, h = item % NH;
+                    const int sl = kl_issued & (RING - 1);
+                    mbar_expect_tx(bars.kvfull(sl), 2 * TILE_BYTES);
+                    tma_load_3d(base + OFF_K + sl * TILE_BYTES, &map_qkv, bars.kvfull(sl), NH * HD + h * HD, kt * BKV, n);
+                    tma_load_3d(base + OFF_V + sl * TILE_BYTES, &map_qkv, bars.kvfull(sl), 2 * NH * HD + h * HD, kt * BKV, n);
+                    ++kl_issued;
+                }
+                // Q: the tile being processed and the next one
+                while (q_issued < total_q && q_issued < it + 2) {
+                    const int li = q_issued / nqt, qt = q_issued % nqt;
+                    const int item = blockIdx.x + li * (int)gridDim.x, n = item / NH, h = item % NH;
+                    mbar_expect_tx(bars.qfull(q_issued & 1), TILE_BYTES);
+                    tma_load_3d(base + OFF_Q + (q_issued & 1) * TILE_BYTES, &map_qkv, bars.qfull(q_issued & 1), h * HD, qt * BQ, n);
+                    ++q_issued;
+                }
+            };
+
+            issue_loads();
+            for (int li = 0; li < my_items; ++li) {
+                const int first_kl = li * (nqt + 2);
+                for (int qt = 0; qt < nqt; ++qt, ++it) {
+                    // S_j = Q K_j^T  (both operands K-major, 128-byte swizzled rows of 64 head dims)
+                    mbar_wait(bars.qfull(it & 1), (uint32_t)((it >> 1) & 1));
+                    if (it > 0) mbar_wait(bars.tfree(), (uint32_t)((it - 1) & 1));    // the previous tile's O has been read
+                    tc_fence_after();
+                    const uint64_t qdesc = tc_smem_desc_sw128(base + OFF_Q + (it & 1) * TILE_BYTES);
 #pragma unroll
-            for (int j = 0; j < NKT; ++j) {
-                mbar_wait(bar_p(j), 0);
-                tc_fence_after();
-                const uint64_t vdesc = tc_smem_desc_sw128(base + OFF_V + j * TILE_BYTES);
+                    for (int j = 0; j < NKT; ++j) {
+                        const int kl = first_kl + qt + j, sl = kl & (RING - 1);
+                        mbar_wait(bars.kvfull(sl), (uint32_t)((kl / RING) & 1));
+                        tc_fence_after();
+                        const uint64_t kdesc = tc_smem_desc_sw128(base + OFF_K + sl * TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < BKV / 16; ++k)
-                    tc_mma_ts(tmem_base + (uint32_t)(j * 128 + 64), tmem_base + (uint32_t)(j * 128 + 8 * k),
-                              vdesc + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0 ? 1u : 0u);
+                        for (int k = 0; k < HD / 16; ++k)
+                            tc_mma_ss(tmem_base + (uint32_t)(j * 128), qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+                        tc_commit(bars.s(j));
+                    }
+                    // O_j = P_j V_j  (A = P_j from TMEM: lane = query, column c = keys 2c, 2c+1; B = V_j MN-major: K = keys are
+                    // the 128-byte rows, 8 keys per 1024-byte swizzle atom: one K = 16 step advances the descriptor by 2048 B)
+#pragma unroll
+                    for (int j = 0; j < NKT; ++j) {
+                        const int kl = first_kl + qt + j, sl = kl & (RING - 1);
+                        mbar_wait(bars.p(j), (uint32_t)(it & 1));
+                        tc_fence_after();
+                        const uint64_t vdesc = tc_smem_desc_sw128(base + OFF_V + sl * TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BKV / 16; ++k)
+                            tc_mma_ts(tmem_base + (uint32_t)(j * 128 + 64), tmem_base + (uint32_t)(j * 128 + 8 * k),
+                                      vdesc + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0 ? 1u : 0u);
+                    }
+                    tc_commit(bars.o());
+                    // once these MMAs have completed, key tile qt-1 of the item (and, after the last query tile, the rest)
+                    // is dead: refill its ring slot with the key tile four ahead, and fetch the Q after next
+                    mbar_wait(bars.o(), (uint32_t)(it & 1));
+                    kl_released = first_kl + (qt + 1 < nqt ? qt + 1 : nqt + 2);
+                    ++it;
+                    issue_loads();
+                    --it;
+                }
             }
-            tc_commit(bar_o);
         }
         __syncwarp();
     } else {
         // ===== softmax warps: thread = query row =====
-        const int r = warp * 32 + lane, q = q0 + r;
-        // visible band of this row in band columns c = key - k0 (0 .. 383)
-        const int lo = max(BKV + r - wl, -k0), hi = min(BKV + r + wr, T - 1 - k0);
+        const int r = warp * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        float m[NKT], l[NKT];
+        int it = 0;
+        for (int item = blockIdx.x; item < items; item += (int)gridDim.x) {
+            const int n = item / NH, h = item % NH;
+            for (int qt = 0; qt < nqt; ++qt, ++it) {
+                const int q0 = qt * BQ, q = q0 + r, k0 = q0 - BKV;
+                // visible band of this row in band columns c = key - k0 (0 .. 383)
+                const int lo = max(BKV + r - wl, -k0), hi = min(BKV + r + wr, T - 1 - k0);
+                const uint32_t ph = (uint32_t)(it & 1);
+                float m[NKT], l[NKT];
 #pragma unroll
-        for (int j = 0; j < NKT; ++j) {
-            const int a = max(lo - j * BKV, 0), b = min(hi - j * BKV, BKV - 1);    // visible columns of tile j: [a, b]
-            mbar_wait(bar_s(j), 0);
-            tc_fence_after();
-            uint32_t s[BKV];
-            // pieces of 32 columns; a piece that no row of this warp sees is not even read
-            bool need[4];
+                for (int j = 0; j < NKT; ++j) {
+                    const int a = max(lo - j * BKV, 0), b = min(hi - j * BKV, BKV - 1);    // visible columns of tile j: [a, b]
+                    mbar_wait(bars.s(j), ph);
+                    tc_fence_after();
+                    uint32_t s[BKV];
+                    // 32-column pieces: 0 = no row of this warp sees it (not read), 2 = every row sees all of it (no
+                    // compares), 1 = mixed
+                    int kind[4];
 #pragma unroll
-            for (int pc = 0; pc < 4; ++pc) {
-                need[pc] = __any_sync(0xffffffffu, a <= pc * 32 + 31 && b >= pc * 32);
-                if (need[pc]) tc_ld_32x32b_x32(lane_addr + (uint32_t)(j * 128 + pc * 32), *reinterpret_cast<uint32_t(*)[32]>(&s[pc * 32]));
-            }
-            tc_wait_ld();
-            float mx = -1e30f;
-#pragma unroll
-            for (int pc = 0; pc < 4; ++pc)
-                if (need[pc]) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int col = pc * 32 + c;
-                        if (col >= a && col <= b) mx = fmaxf(mx, __uint_as_float(s[col]));
+                    for (int pc = 0; pc < 4; ++pc) {
+                        const bool any = __any_sync(0xffffffffu, a <= pc * 32 + 31 && b >= pc * 32);
+                        const bool all = __all_sync(0xffffffffu, a <= pc * 32 && b >= pc * 32 + 31);
+                        kind[pc] = all ? 2 : (any ? 1 : 0);
+                        if (any) tc_ld_32x32b_x32(lane_addr + (uint32_t)(j * 128 + pc * 32), *reinterpret_cast<uint32_t(*)[32]>(&s[pc * 32]));
                     }
+                    tc_wait_ld();
+                    float mx = -1e30f;
+#pragma unroll
+                    for (int pc = 0; pc < 4; ++pc) {
+                        if (kind[pc] == 2) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(s[pc * 32 + c]));
+                        } else if (kind[pc] == 1) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const int col = pc * 32 + c;
+                                if (col >= a && col <= b) mx = fmaxf(mx, __uint_as_float(s[col]));
+                            }
+                        }
+                    }
+                    m[j] = mx;
+                    const float mb = mx * scale_log2e;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {          // 64 scores -> 32 fp16 pairs -> P columns [32*half, +32)
+                        uint32_t pk[32];
+#pragma unroll
+                        for (int pp = 0; pp < 2; ++pp) {
+                            const int pc = half * 2 + pp;
+                            if (kind[pc] == 2) {
+#pragma unroll
+                                for (int c2 = 0; c2 < 16; ++c2) {
+                                    const int col = pc * 32 + 2 * c2;
+                                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[col]), scale_log2e, -mb));
+                                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[col + 1]), scale_log2e, -mb));
+                                    sum += p0 + p1;
+                                    const __half2 h2 = __floats2half2_rn(p0, p1);
+                                    pk[pp * 16 + c2] = *reinterpret_cast<const uint32_t*>(&h2);
+                                }
+                            } else if (kind[pc] == 1) {
+#pragma unroll
+                                for (int c2 = 0; c2 < 16; ++c2) {
+                                    const int col = pc * 32 + 2 * c2;
+                                    float p0 = 0.f, p1 = 0.f;
+                                    if (col >= a && col <= b) p0 = ex2_approx(fmaf(__uint_as_float(s[col]), scale_log2e, -mb));
+                                    if (col + 1 >= a && col + 1 <= b) p1 = ex2_approx(fmaf(__uint_as_float(s[col + 1]), scale_log2e, -mb));
+                                    sum += p0 + p1;
+                                    const __half2 h2 = __floats2half2_rn(p0, p1);
+                                    pk[pp * 16 + c2] = *reinterpret_cast<const uint32_t*>(&h2);
+                                }
+                            } else {
+#pragma unroll
+                                for (int c2 = 0; c2 < 16; ++c2) pk[pp * 16 + c2] = 0u;
+                            }
+                        }
+                        tc_st_32x32b_x32(lane_addr + (uint32_t)(j * 128 + half * 32), pk);
+                    }
+                    l[j] = sum;
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars.p(j));
                 }
-            m[j] = mx;
-            const float mb = mx * scale_log2e;
-            float sum = 0.f;
+                // ===== epilogue: combine the three partial softmaxes of the row =====
+                const float M = fmaxf(fmaxf(m[0], m[1]), m[2]);
+                float f[NKT], L = 0.f;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {          // 64 scores -> 32 fp16 pairs -> P columns [32*half, +32)
-                uint32_t pk[32];
-#pragma unroll
-                for (int c2 = 0; c2 < 32; ++c2) {
-                    const int col = half * 64 + 2 * c2, pc = col >> 5;
-                    float p0 = 0.f, p1 = 0.f;
-                    if (need[pc]) {
-                        if (col >= a && col <= b) p0 = ex2_approx(fmaf(__uint_as_float(s[col]), scale_log2e, -mb));
-                        if (col + 1 >= a && col + 1 <= b) p1 = ex2_approx(fmaf(__uint_as_float(s[col + 1]), scale_log2e, -mb));
-                    }
-                    sum += p0 + p1;
-                    const __half2 h2 = __floats2half2_rn(p0, p1);
-                    pk[c2] = *reinterpret_cast<const uint32_t*>(&h2);
+                for (int j = 0; j < NKT; ++j) {
+                    f[j] = ex2_approx(fmaxf((m[j] - M) * scale_log2e, -126.f));
+                    if (m[j] <= -1e30f) f[j] = 0.f;
+                    L = fmaf(l[j], f[j], L);
                 }
-                tc_st_32x32b_x32(lane_addr + (uint32_t)(j * 128 + half * 32), pk);
-            }
-            l[j] = sum;
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_p(j));
-        }
-        // ===== epilogue: combine the three partial softmaxes of the row =====
-        const float M = fmaxf(fmaxf(m[0], m[1]), m[2]);
-        float f[NKT], L = 0.f;
+                const float inv = L > 0.f ? 1.0f / L : 0.f;
+                f[0] *= inv; f[1] *= inv; f[2] *= inv;
+                mbar_wait(bars.o(), ph);
+                tc_fence_after();
+                __half* dst = out + ((size_t)n * T + q) * (size_t)(NH * HD) + h * HD;
 #pragma unroll
-        for (int j = 0; j < NKT; ++j) {
-            f[j] = ex2_approx(fmaxf((m[j] - M) * scale_log2e, -126.f));
-            if (m[j] <= -1e30f) f[j] = 0.f;
-            L = fmaf(l[j], f[j], L);
-        }
-        const float inv = L > 0.f ? 1.0f / L : 0.f;
-        mbar_wait(bar_o, 0);
-        tc_fence_after();
-        __half* dst = out + ((size_t)n * T + q) * (size_t)(NH * HD) + h * HD;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t o0[32], o1[32], o2[32];
-            tc_ld_32x32b_x32(lane_addr + (uint32_t)(0 * 128 + 64 + half * 32), o0);
-            tc_ld_32x32b_x32(lane_addr + (uint32_t)(1 * 128 + 64 + half * 32), o1);
-            tc_ld_32x32b_x32(lane_addr + (uint32_t)(2 * 128 + 64 + half * 32), o2);
-            tc_wait_ld();
-            if (q < T) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    __half2 hh[4];
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const int c = g * 8 + 2 * p;
-                        const float v0 = (__uint_as_float(o0[c]) * f[0] + __uint_as_float(o1[c]) * f[1] + __uint_as_float(o2[c]) * f[2]) * inv;
-                        const float v1 = (__uint_as_float(o0[c + 1]) * f[0] + __uint_as_float(o1[c + 1]) * f[1] + __uint_as_float(o2[c + 1]) * f[2]) * inv;
-                        hh[p] = __floats2half2_rn(v0, v1);
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t o0[32], o1[32], o2[32];
+                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(0 * 128 + 64 + half * 32), o0);
+                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(1 * 128 + 64 + half * 32), o1);
+                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(2 * 128 + 64 + half * 32), o2);
+                    tc_wait_ld();
+                    if (half == 1) {            // all of this tile's TMEM has been read: the next tile's MMAs may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bars.tfree());
                     }
-                    *reinterpret_cast<uint4*>(dst + half * 32 + g * 8) = *reinterpret_cast<const uint4*>(hh);
+                    if (q < T) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            __half2 hh[4];
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const int c = g * 8 + 2 * p;
+                                const float v0 = __uint_as_float(o0[c]) * f[0] + __uint_as_float(o1[c]) * f[1] + __uint_as_float(o2[c]) * f[2];
+                                const float v1 = __uint_as_float(o0[c + 1]) * f[0] + __uint_as_float(o1[c + 1]) * f[1] + __uint_as_float(o2[c + 1]) * f[2];
+                                hh[p] = __floats2half2_rn(v0, v1);
+                            }
+                            *reinterpret_cast<uint4*>(dst + half * 32 + g * 8) = *reinterpret_cast<const uint4*>(hh);
+                        }
+                    }
                 }
             }
         }
@@ -248,9 +338,13 @@ int launch_attention_tc(const __half* qkv, __half* out, int N, int T, int NH, in
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "attention: cuTensorMapEncodeTiled failed (%d)", (int)r);
     B200_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    dim3 grid((T + BQ - 1) / BQ, NH, N);
+    int dev = 0, sms = 0;
+    B200_CHECK_CUDA(cudaGetDevice(&dev));
+    B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int items = N * NH;
+    const int grid = items < sms ? items : sms;
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
-    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map, out, T, NH, wl, wr, scale_log2e);
+    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map, out, N, T, NH, wl, wr, scale_log2e);
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -127,7 +127,8 @@ struct Bars {
 // blk % 4 of accumulator blk / 4), all 16 chunks of the sub-tile.
 // VARIANT (B200_LSTM_DEBUG): 0 = product; 3 = product + timeline.
 template <int VARIANT, int EXCH>
-__device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned char* __restrict__ hx, int T, int nb,
+__device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned char* __restrict__ hx,
+                                              const __half* __restrict__ gx_sub, int T, int nb,
                                               int reverse, uint32_t rank, int sub, int ew, uint32_t tmem_base,
                                               uint32_t base, unsigned char* gbase, Bars bars, int lane, int ablate) {
     const int r = lane >> 2, q = lane & 3;
@@ -229,6 +230,14 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned c
             if (y_ok && !(ablate & 2)) *reinterpret_cast<uint4*>(y_lane + (size_t)t * (NB * H)) = chunk;   // -> Y[t], off the critical path
         }
         if (tl && ew == 0) g_timeline6[ts][5] = clock64();
+        // gx refill: this warp is past the accumulator barrier of `step`, so the h tile (sub, step) was complete, so every
+        // epilogue warp of the sub-tile has sent -- and therefore consumed its gx of -- step-1: that ring slot is free
+        if (ew == 0 && step + GXD - 1 < T && !(ablate & 1) && elect_one_sync()) {
+            const int s2 = step + GXD - 1, t2 = reverse ? (T - 1 - s2) : s2, slot2 = s2 & (GXD - 1);
+            const uint32_t bar = bars.gxfull(sub, slot2);
+            mbar_expect_tx(bar, GXS);
+            bulk_load_global(base + OFF_GX + (uint32_t)(sub * GXD + slot2) * GXS, gx_sub + (size_t)t2 * (CS * NB * ROWS), GXS, bar);
+        }
         __syncwarp();
     }
 }
@@ -236,8 +245,9 @@ __device__ __forceinline__ void epilogue_warp(__half* __restrict__ y, unsigned c
 // Staging-buffer reuse: the block staged at step s (parity p, sub-tile u) is read asynchronously by 6 bulk copies.  It
 // is overwritten at step s+2, after this CTA has seen its own h tile (u, s+2) complete, which needs every peer's
 // epilogue of (u, s+1), which needs that peer's h tile (u, s+1) complete -- i.e. all copies of step s landed.
-// gx ring reuse: the MMA thread refills the slot of step s-1 (with step s+GXD-1) after it has seen the h tile (u, s)
-// complete, which needs this CTA's own epilogue warps of (u, s-1) to have sent, i.e. to have consumed gx (u, s-1).
+// gx ring reuse: epilogue warp 0 of sub-tile u refills the slot of step s-1 (with step s+GXD-1) during step s, after the
+// accumulator barrier of (u, s): the MMAs of (u, s) were issued after the h tile (u, s) was complete, which needs this
+// CTA's own epilogue warps of (u, s-1) to have sent, i.e. to have consumed gx (u, s-1).
 // TMEM accumulator reuse: the MMAs of (u, s+1) are issued after the h tile (u, s+1) is complete, i.e. after every
 // epilogue warp of (u, s) has drained its accumulator block (tcgen05.wait::ld precedes the send).
 template <int VARIANT, int EXCH>
@@ -331,7 +341,7 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
                 if (elect_one_sync()) {
                     if (step > 0) {
                         if (step + 2 < T) mbar_expect_tx(hbar, HT);   // re-arm for the fill during step+1
-                        fence_proxy_async_smem();
+                        // (no proxy fence: the h tile was written by bulk copies and is read by the tensor core, both async proxy)
                     }
                     if (VARIANT == 3 && sub == 0 && blockIdx.x == 0) {
                         g_timeline6[step % TL_STEPS][0] = clock64();
@@ -353,7 +363,8 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
                     }
                     tc_commit(bars.dfull(sub));
                     if (VARIANT == 3 && sub == 0 && blockIdx.x == 0) g_timeline6[step % TL_STEPS][1] = clock64();
-                    if (step + GXD - 1 < T && !(ablate & 1)) load_gx(step + GXD - 1, sub);   // into the slot of step-1 (consumed, see above)
+                    // the gx refill for step + GXD - 1 is issued by epilogue warp 0 of the sub-tile (keeps ~100 cycles per
+                    // sub-tile out of this loop: the issuing warp's ~3 x 900 cycles per step bounded the step time)
                 }
                 __syncwarp();
             }
@@ -361,7 +372,8 @@ lstm_rec_tc6_kernel(const __half* __restrict__ gx, const __half* __restrict__ wh
     } else {
         const int sub = warp / EW, ew = warp % EW;
         if (sub < nsub)
-            epilogue_warp<VARIANT, EXCH>(y, hx, T, nb, reverse, rank, sub, ew, tmem_base, base, gbase, bars, lane, ablate);
+            epilogue_warp<VARIANT, EXCH>(y, hx, gx + (size_t)rank * (NB * ROWS) + (size_t)sub * (SN * ROWS), T, nb, reverse, rank, sub,
+                                         ew, tmem_base, base, gbase, bars, lane, ablate);
     }
 
     tc_fence_before();
