@@ -41,6 +41,9 @@ int launch_crf_decode(const __half* scores, int N, int T, int state_len, float b
 
 // one message buffer per host thread: the reference drives this path from background threads (bonito/multiprocessing.py:118-122),
 // so a failing call must read back its own message, not another thread's
+int launch_crf_beam_search(const __half* scores, int N, int T, int state_len, float blank, int width, float cut, float qscale,
+                           float qbias, void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream);
+
 static thread_local char g_err[1024] = "";
 
 void b200_set_error(const char* fmt, ...) {
@@ -220,6 +223,15 @@ int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank
     B200_REQUIRE(scores && workspace && moves && sequence && qstring, "crf_decode: null pointer argument");
     return launch_crf_decode((const __half*)scores, n, t, state_len, blank_score, qscale, qbias, workspace,
                              (uint8_t*)moves, (uint8_t*)sequence, (uint8_t*)qstring, (cudaStream_t)stream);
+}
+
+int b200_crf_beam_search(const void* scores, int n, int t, int state_len, float blank_score, int beam_width, float beam_cut,
+                         float qscale, float qbias, void* workspace, void* moves, void* sequence, void* qstring, void* stream) {
+    B200_REQUIRE(n >= 0 && t >= 0, "beam_search: bad sizes n=%d t=%d", n, t);
+    if (n == 0 || t == 0) return 0;
+    B200_REQUIRE(scores && workspace && moves && sequence && qstring, "beam_search: null pointer argument");
+    return launch_crf_beam_search((const __half*)scores, n, t, state_len, blank_score, beam_width, beam_cut, qscale, qbias,
+                                  workspace, (uint8_t*)moves, (uint8_t*)sequence, (uint8_t*)qstring, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -336,6 +336,218 @@ int launch_decode(const __half* scores, int N, int T, float blank, float qscale,
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Beam search behind the koi.decode.beam_search call contract (bonito/crf/basecall.py:36-40).  koi's decoder is a closed
+// binary with no pinned outputs, so this is THIS repository's beam search (restated for the tests by
+// oracle/crf_oracle.py::beam_search_native), offered next to the exact posterior-Viterbi decoder above:
+// a backward-guided prefix search over (sequence, k-mer state) entries, one WARP per chunk, one LANE per beam entry
+// (beam_width <= 32).  Per frame a lane spawns a "stay" and four "move" candidates; a stay candidate and the move candidate
+// that spells the same sequence are merged by log-add; the 160 candidates are ranked by forward score + beta'_{t+1}[state]
+// (the backward scores the forward-backward kernel left in the workspace), cut at `beam_cut` below the best, and the best
+// `beam_width` survive (ties: lower parent entry, stay before moves, lower base).  All scores in log2 units.
+// Runs after crf_decode_kernel on the same workspace: it reads beta' and the posterior move mass (qualities) and reuses
+// the back-pointer area (32 bytes per frame).
+__device__ __forceinline__ float lse2_2(float a, float b) {
+    const float hi = fmaxf(a, b), lo = fminf(a, b);
+    return hi + lg2_approx(1.0f + ex2_approx(lo - hi));
+}
+
+template <int S>
+__global__ void __launch_bounds__(128)
+crf_beam_kernel(const __half* __restrict__ scores, int N, int T, float blank, int width, float cut, float qscale,
+                float qbias, const float* __restrict__ ws_beta, uint8_t* __restrict__ ws_bp,
+                const float* __restrict__ ws_pm, uint8_t* __restrict__ moves, uint8_t* __restrict__ seq,
+                uint8_t* __restrict__ qual) {
+    constexpr int Q = S / 4;
+    constexpr unsigned long long MULT = 0x9E3779B97F4A7C15ull;
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const __half* sc = scores + (size_t)n * T * S * 4;
+    const float* beta = ws_beta + (size_t)n * (T + 1) * S;
+    uint8_t* bp = ws_bp + (size_t)n * T * S;                 // [T][32] used
+    const float* pm = ws_pm + (size_t)n * T * 4;
+    const float blank2 = blank * LOG2E, cut2 = cut * LOG2E;
+    const unsigned FULL = 0xffffffffu;
+
+    // ---- start beam: the `width` best start states by beta'_0 (ties: lower state) ----
+    unsigned long long h = 0;
+    int st = 0;
+    float a = 0.f;
+    bool valid = false;
+    {
+        constexpr int PER = S / 32;                           // states per lane: lane l owns states l*PER .. l*PER+PER-1
+        float v[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) v[i] = beta[lane * PER + i];
+        for (int r = 0; r < width; ++r) {
+            float best = -INFINITY;
+            int bi = 0;
+#pragma unroll
+            for (int i = 0; i < PER; ++i)
+                if (v[i] > best) { best = v[i]; bi = i; }
+            int bidx = lane * PER + bi;
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULL, best, o);
+                const int oi = __shfl_xor_sync(FULL, bidx, o);
+                if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+            }
+            if (bidx / PER == lane) {
+#pragma unroll
+                for (int i = 0; i < PER; ++i)
+                    if (i == bidx % PER) v[i] = -INFINITY;
+            }
+            if (lane == r && best > -INFINITY) { h = (unsigned long long)bidx + 1ull; st = bidx; a = 0.f; valid = true; }
+        }
+    }
+
+    // ---- frames ----
+    for (int t = 0; t < T; ++t) {
+        const __half* m = sc + (size_t)t * S * 4;
+        const float* bn = beta + (size_t)(t + 1) * S;
+        float csc[5], key[5];
+        int cst[5], ccode[5], cpar[5];
+        unsigned long long ch[5];
+        const int sq = st % Q, j = st / Q;
+        const float4 b4 = *reinterpret_cast<const float4*>(bn + sq * 4);
+        const float bmove[4] = {b4.x, b4.y, b4.z, b4.w};
+        ch[0] = h; cst[0] = st; csc[0] = a + blank2; ccode[0] = 0; cpar[0] = lane;
+        key[0] = valid ? csc[0] + bn[st] : -INFINITY;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int s2 = sq * 4 + b;
+            ch[1 + b] = h * MULT + (unsigned long long)(b + 1);
+            cst[1 + b] = s2;
+            csc[1 + b] = fmaf(__half2float(m[s2 * 4 + j]), LOG2E, a);
+            ccode[1 + b] = 1 + b; cpar[1 + b] = lane;
+            key[1 + b] = valid ? csc[1 + b] + bmove[b] : -INFINITY;
+        }
+        // merge: the stay candidate of entry jj with the move candidate (of some entry) that spells the same sequence
+        for (int jj = 0; jj < 32; ++jj) {
+            const unsigned long long hj = __shfl_sync(FULL, h, jj);
+            const bool vj = __shfl_sync(FULL, (int)valid, jj) != 0;
+            if (!vj) continue;                                         // warp-uniform
+            int mb = -1;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (valid && key[1 + b] > -INFINITY && ch[1 + b] == hj && mb < 0) mb = b;
+            const unsigned hit = __ballot_sync(FULL, mb >= 0);
+            if (hit == 0) continue;                                    // warp-uniform
+            const int src = __ffs(hit) - 1;
+            float msc = 0.f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (b == mb) msc = csc[1 + b];
+            msc = __shfl_sync(FULL, msc, src);
+            const int mbase = __shfl_sync(FULL, mb, src);
+            if (lane == src) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (b == mb) key[1 + b] = -INFINITY;
+            }
+            if (lane == jj) {
+                const float stay = csc[0];
+                csc[0] = lse2_2(stay, msc);
+                if (msc > stay) { ccode[0] = 1 + mbase; cpar[0] = src; }
+                key[0] = csc[0] + bn[st];
+            }
+        }
+        // cut
+        float kbest = fmaxf(fmaxf(fmaxf(key[0], key[1]), fmaxf(key[2], key[3])), key[4]);
+        for (int o = 16; o > 0; o >>= 1) kbest = fmaxf(kbest, __shfl_xor_sync(FULL, kbest, o));
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+            if (key[c] < kbest - cut2) key[c] = -INFINITY;
+        // selection: `width` rounds of (lane-local best, warp arg-max by (key desc, candidate index asc))
+        unsigned long long nh = 0;
+        int nst = 0, nbp = 0;
+        float na = 0.f;
+        bool nvalid = false;
+        for (int r = 0; r < width; ++r) {
+            float lk = key[0];
+            int lc = 0;
+#pragma unroll
+            for (int c = 1; c < 5; ++c)
+                if (key[c] > lk) { lk = key[c]; lc = c; }
+            float wk = lk;
+            int wi = lane * 5 + lc;
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ok = __shfl_xor_sync(FULL, wk, o);
+                const int oi = __shfl_xor_sync(FULL, wi, o);
+                if (ok > wk || (ok == wk && oi < wi)) { wk = ok; wi = oi; }
+            }
+            if (!(wk > -INFINITY)) break;                              // warp-uniform: no candidate left
+            const int wl = wi / 5, wc = wi % 5;
+            unsigned long long xh = 0;
+            int xs = 0, xb = 0;
+            float xa = 0.f;
+#pragma unroll
+            for (int c = 0; c < 5; ++c)
+                if (c == wc) { xh = ch[c]; xs = cst[c]; xa = csc[c]; xb = cpar[c] | (ccode[c] << 5); }
+            xh = __shfl_sync(FULL, xh, wl);
+            xs = __shfl_sync(FULL, xs, wl);
+            xa = __shfl_sync(FULL, xa, wl);
+            xb = __shfl_sync(FULL, xb, wl);
+            if (lane == wl) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c)
+                    if (c == wc) key[c] = -INFINITY;
+            }
+            if (lane == r) { nh = xh; nst = xs; na = xa; nbp = xb; nvalid = true; }
+        }
+        // renormalise on the best surviving score
+        float amax = nvalid ? na : -INFINITY;
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
+        h = nh; st = nst; a = na - amax; valid = nvalid;
+        bp[(size_t)t * 32 + lane] = (uint8_t)nbp;
+    }
+
+    // ---- best final entry (ties: lower lane), trace-back ----
+    float fa = valid ? a : -INFINITY;
+    int fi = lane;
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, fa, o);
+        const int oi = __shfl_xor_sync(FULL, fi, o);
+        if (ov > fa || (ov == fa && oi < fi)) { fa = ov; fi = oi; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int r = fi;
+        for (int t = T - 1; t >= 0; --t) {
+            const int e = bp[(size_t)t * 32 + r];
+            const int code = e >> 5;
+            uint8_t mv = 0, sq_ = 0, ql = 0;
+            if (code) {
+                const int base = code - 1;
+                const float p = pm[(size_t)t * 4 + base];
+                const float err = fmaxf(1.0f - p, 1e-4f);
+                int qi = (int)rintf(-10.0f * log10f(err) * qscale + qbias) + 33;
+                qi = min(max(qi, 33), 126);
+                mv = 1; sq_ = (uint8_t)("ACGT"[base]); ql = (uint8_t)qi;
+            }
+            moves[(size_t)n * T + t] = mv;
+            seq[(size_t)n * T + t] = sq_;
+            qual[(size_t)n * T + t] = ql;
+            r = e & 31;
+        }
+    }
+}
+
+template <int S>
+int launch_beam(const __half* scores, int N, int T, float blank, int width, float cut, float qscale, float qbias,
+                void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream) {
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    size_t off = 0;
+    float* beta = reinterpret_cast<float*>(ws + off); off += align256((size_t)N * (T + 1) * S * sizeof(float));
+    off += align256((size_t)N * (T + 1) * sizeof(double));
+    float* pm = reinterpret_cast<float*>(ws + off); off += align256((size_t)N * T * 4 * sizeof(float));
+    uint8_t* bp = ws + off;
+    crf_beam_kernel<S><<<(N + 3) / 4, 128, 0, stream>>>(scores, N, T, blank, width, cut, qscale, qbias, beta, bp, pm, moves, seq, qual);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 size_t crf_decode_workspace_bytes(int N, int T, int state_len) {
@@ -355,5 +567,20 @@ int launch_crf_decode(const __half* scores, int N, int T, int state_len, float b
         default:
             b200_set_error("crf_decode: state_len %d is not supported (3, 4, 5)", state_len);
             return -2;
+    }
+}
+
+// exact forward-backward first (it fills beta' and the move mass), then the beam search over the same workspace
+int launch_crf_beam_search(const __half* scores, int N, int T, int state_len, float blank, int width, float cut, float qscale,
+                           float qbias, void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream) {
+    if (N == 0 || T == 0) return 0;
+    B200_REQUIRE(width >= 1 && width <= 32, "beam_search: beam_width %d is not supported (1..32: one lane per beam entry)", width);
+    int rc = launch_crf_decode(scores, N, T, state_len, blank, qscale, qbias, workspace, moves, seq, qual, stream);
+    if (rc) return rc;
+    switch (state_len) {
+        case 3: return launch_beam<64>(scores, N, T, blank, width, cut, qscale, qbias, workspace, moves, seq, qual, stream);
+        case 4: return launch_beam<256>(scores, N, T, blank, width, cut, qscale, qbias, workspace, moves, seq, qual, stream);
+        case 5: return launch_beam<1024>(scores, N, T, blank, width, cut, qscale, qbias, workspace, moves, seq, qual, stream);
+        default: return -2;
     }
 }

@@ -606,11 +606,13 @@ class CrfDecoder:
     def __init__(self):
         self._ws_by_device = {}     # one workspace per (device, host thread): basecall() decodes on background threads
 
-    def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0, events=None, out=None, slot=0):
+    def __call__(self, scores, state_len, blank_score=2.0, qscale=1.0, qbias=0.0, events=None, out=None, slot=0, beam=None):
+        """`beam=(beam_width, beam_cut)`: run the beam search (after the forward-backward pass) instead of the exact
+        posterior-Viterbi trace-back."""
         with torch.cuda.device(scores.device):
-            return self._call(scores, state_len, blank_score, qscale, qbias, events, out, slot)
+            return self._call(scores, state_len, blank_score, qscale, qbias, events, out, slot, beam)
 
-    def _call(self, scores, state_len, blank_score, qscale, qbias, events, out, slot=0):
+    def _call(self, scores, state_len, blank_score, qscale, qbias, events, out, slot=0, beam=None):
         """-> (moves, sequence, qstring) uint8 [N, T] on the device; `out`: optional uint8 [3, N, T] to write them into."""
         n, t, c = scores.shape
         if c != 4 ** (state_len + 1):
@@ -631,5 +633,8 @@ class CrfDecoder:
             ws = self._ws_by_device[key] = torch.empty(need, dtype=torch.uint8, device=scores.device)
         outs = list(out) if out is not None else [torch.empty(n, t, dtype=torch.uint8, device=scores.device) for _ in range(3)]
         with _Stage("crf_decode", events):
-            native.crf_decode(scores, state_len, blank_score, qscale, qbias, ws, *outs)
+            if beam is None:
+                native.crf_decode(scores, state_len, blank_score, qscale, qbias, ws, *outs)
+            else:
+                native.crf_beam_search(scores, state_len, blank_score, beam[0], beam[1], qscale, qbias, ws, *outs)
         return tuple(outs)  # moves, sequence, qstring

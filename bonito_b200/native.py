@@ -49,6 +49,8 @@ SIGNATURES = {
     "b200_debug_exchange_bench": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "b200_crf_beam_search": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_crf_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
@@ -269,4 +271,16 @@ def crf_decode(scores, state_len, blank_score, qscale, qbias, workspace, moves, 
                                  float(qbias), _ptr(workspace), _ptr(moves), _ptr(sequence), _ptr(qstring),
                                  _stream(stream))
     _check(rc, "b200_crf_decode")
+    return moves, sequence, qstring
+
+
+def crf_beam_search(scores, state_len, blank_score, beam_width, beam_cut, qscale, qbias, workspace, moves, sequence, qstring,
+                    stream=None):
+    lib = require()
+    n, t, _ = scores.shape
+    with torch.cuda.device(scores.device):
+        rc = lib.b200_crf_beam_search(_ptr(scores), n, t, state_len, float(blank_score), int(beam_width), float(beam_cut),
+                                      float(qscale), float(qbias), _ptr(workspace), _ptr(moves), _ptr(sequence),
+                                      _ptr(qstring), _stream(stream))
+    _check(rc, "b200_crf_beam_search")
     return moves, sequence, qstring

@@ -205,6 +205,16 @@ size_t b200_crf_decode_workspace_bytes(int n, int t, int state_len);
 int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank_score, float qscale, float qbias,
                     void* workspace, void* moves, void* sequence, void* qstring, void* stream);
 
+/*
+ * Beam-search decode with the argument meaning of koi.decode.beam_search (bonito/crf/basecall.py:36-40): beam_width entries
+ * (1..32), candidates more than beam_cut (natural-log units) below the best are dropped.  koi itself is a closed binary with
+ * no pinned outputs, so this is this library's own backward-guided prefix beam search (oracle: crf_oracle.beam_search_native);
+ * the exact posterior-Viterbi decoder b200_crf_decode stays the default.  Same scores / outputs / workspace as b200_crf_decode
+ * (the forward-backward pass runs first and provides the look-ahead scores and the qualities).
+ */
+int b200_crf_beam_search(const void* scores, int n, int t, int state_len, float blank_score, int beam_width, float beam_cut,
+                         float qscale, float qbias, void* workspace, void* moves, void* sequence, void* qstring, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

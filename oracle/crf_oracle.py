@@ -252,3 +252,93 @@ def decode_native(scores_ntc, state_len, blank_score=2.0, qscale=1.0, qbias=0.0,
     seq = np.where(move, letters[base], 0).T.astype(np.uint8)
     qual = np.where(move, q, 0).T.astype(np.uint8)
     return moves, seq, qual, mass.transpose(1, 0, 2)
+
+
+# --------------------------------------------------------------------------------------------------
+# beam search  (koi.decode.beam_search call contract, bonito/crf/basecall.py:36-40)
+# --------------------------------------------------------------------------------------------------
+# koi's decoder is a closed binary with no pinned outputs ("parity unpinned"), so this restates
+# the ALGORITHM THIS REPOSITORY SHIPS behind the same signature -- a backward-guided prefix beam search over the k-mer
+# CRF -- and is the checker of the CUDA kernel, not a parity claim against koi:
+#   * a beam entry is a (sequence, k-mer state) pair: identified by a 64-bit hash of the emitted bases + start state;
+#   * per frame every entry spawns "stay" (blank score) and four "move" candidates (state' = (state % Q) * 4 + base, score
+#     M_t[state' * 4 + state / Q]); a stay candidate and a move candidate that reach the same sequence are merged by
+#     log-add (the two alignments of that prefix), recording the larger one as the back-pointer;
+#   * candidates are ranked by forward score + beta'_{t+1}[state'] (the exact backward scores of the forward-backward pass
+#     as look-ahead), candidates more than `beam_cut` below the best are dropped, the best `beam_width` survive
+#     (ties: lower candidate index = lower parent entry, stay before moves, lower base);
+#   * the start beam is the `beam_width` best start states by beta'_0; the answer is the trace-back of the best final entry.
+BEAM_HASH_MULT = np.uint64(0x9E3779B97F4A7C15)
+
+
+def beam_search_native(scores_ntc, state_len, blank_score=2.0, beam_width=32, beam_cut=100.0, n_base=4):
+    """scores [N, T, S*4] (no blanks) -> (moves, bases) uint8 [N, T]; bases: 0 = no emission, else 1 + base."""
+    x = np.asarray(scores_ntc, dtype=np.float32)
+    N, T, C = x.shape
+    S = n_base ** state_len
+    Q = S // n_base
+    idx = crf_idx(state_len, n_base)
+    Ms = expand_blanks(x.astype(np.float64).transpose(1, 0, 2), blank_score, n_base).reshape(T, N, S, n_base + 1)
+    _, beta = fwd_bwd(Ms, idx, "log")                         # [T+1, N, S]
+    beta = (beta - beta[:, :, :1]).astype(np.float32)         # re-centred on state 0 per frame, as the kernel keeps it
+    blank = np.float32(blank_score)
+    cut = np.float32(beam_cut)
+    moves = np.zeros((N, T), dtype=np.uint8)
+    bases = np.zeros((N, T), dtype=np.uint8)
+    W = beam_width
+    for n in range(N):
+        order = np.argsort(-beta[0, n], kind="stable")[:W]
+        bh = (order.astype(np.uint64) + np.uint64(1))
+        bs = order.astype(np.int64)
+        bsc = np.zeros(len(order), dtype=np.float32)
+        bp_parent = np.zeros((T, W), dtype=np.int64)
+        bp_code = np.zeros((T, W), dtype=np.int64)
+        counts = np.zeros(T, dtype=np.int64)
+        for t in range(T):
+            nb = len(bs)
+            m = x[n, t]
+            # candidates in index order: entry-major, slot 0 = stay, 1 + b = move with base b
+            ch = np.empty((nb, 5), dtype=np.uint64)
+            cs = np.empty((nb, 5), dtype=np.int64)
+            csc = np.empty((nb, 5), dtype=np.float32)
+            ch[:, 0], cs[:, 0], csc[:, 0] = bh, bs, bsc + blank
+            with np.errstate(over="ignore"):
+                for b in range(4):
+                    s2 = (bs % Q) * 4 + b
+                    ch[:, 1 + b] = bh * BEAM_HASH_MULT + np.uint64(b + 1)
+                    cs[:, 1 + b] = s2
+                    csc[:, 1 + b] = bsc + m[s2 * 4 + bs // Q]
+            alive = np.ones((nb, 5), dtype=bool)
+            code = np.tile(np.arange(5), (nb, 1))
+            parent = np.tile(np.arange(nb)[:, None], (1, 5))
+            # merge: the stay candidate of entry j with the move candidate that spells the same sequence
+            for j in range(nb):
+                hit = np.argwhere((ch[:, 1:] == ch[j, 0]) & alive[:, 1:])
+                if len(hit):
+                    i, b = hit[0]
+                    a, c = csc[j, 0], csc[i, 1 + b]
+                    hi_, lo_ = (a, c) if a >= c else (c, a)
+                    csc[j, 0] = np.float32(hi_ + np.log1p(np.exp(np.float32(lo_ - hi_), dtype=np.float32), dtype=np.float32))
+                    if c > a:
+                        code[j, 0], parent[j, 0] = 1 + b, i
+                    alive[i, 1 + b] = False
+            key = np.where(alive, csc + beta[t + 1, n][cs], -np.inf).astype(np.float32)
+            best = key.max()
+            key = np.where(key < best - cut, -np.inf, key)
+            flat = np.argsort(-key.reshape(-1), kind="stable")
+            flat = flat[np.isfinite(key.reshape(-1)[flat])][:W]
+            sel_i, sel_c = flat // 5, flat % 5
+            new_sc = csc[sel_i, sel_c]
+            counts[t] = len(flat)
+            bp_parent[t, :len(flat)] = parent[sel_i, sel_c]
+            bp_code[t, :len(flat)] = code[sel_i, sel_c]
+            bh, bs = ch[sel_i, sel_c], cs[sel_i, sel_c]
+            bsc = (new_sc - new_sc.max()).astype(np.float32)
+        r = int(np.argmax(bsc))           # first maximum = lowest entry
+        for t in range(T - 1, -1, -1):
+            c = bp_code[t, r]
+            if c:
+                moves[n, t] = 1
+                bases[n, t] = c           # 1 + base
+            r = bp_parent[t, r]
+    return moves, bases
