@@ -559,6 +559,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+        if os.environ.get("B200_PIN", "1") != "0":   # one slice of the host cores per rank (8 Python processes per node)
+            from bonito_b200.distributed import pin_to_local_cores
+            pin_to_local_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     ctx = Ctx(args, rank, local_rank, world, device)
     peaks = load_peaks()
 

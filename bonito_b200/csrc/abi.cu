@@ -44,6 +44,8 @@ int launch_crf_decode(const __half* scores, int N, int T, int state_len, float b
 int launch_crf_beam_search(const __half* scores, int N, int T, int state_len, float blank, int width, float cut, float qscale,
                            float qbias, void* workspace, uint8_t* moves, uint8_t* seq, uint8_t* qual, cudaStream_t stream);
 
+int launch_lstm_crf_fwd(const b200_lstm_crf_plan* p, const __half* x, __half* scores, cudaStream_t stream);
+
 static thread_local char g_err[1024] = "";
 
 void b200_set_error(const char* fmt, ...) {
@@ -223,6 +225,10 @@ int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank
     B200_REQUIRE(scores && workspace && moves && sequence && qstring, "crf_decode: null pointer argument");
     return launch_crf_decode((const __half*)scores, n, t, state_len, blank_score, qscale, qbias, workspace,
                              (uint8_t*)moves, (uint8_t*)sequence, (uint8_t*)qstring, (cudaStream_t)stream);
+}
+
+int b200_lstm_crf_fwd(const b200_lstm_crf_plan* plan, const void* x, void* scores, void* stream) {
+    return launch_lstm_crf_fwd(plan, (const __half*)x, (__half*)scores, (cudaStream_t)stream);
 }
 
 int b200_crf_beam_search(const void* scores, int n, int t, int state_len, float blank_score, int beam_width, float beam_cut,

@@ -176,15 +176,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                 // visible band of this row in band columns c = key - k0 (0 .. 383)
                 const int lo = max(BKV + r - wl, -k0), hi = min(BKV + r + wr, T - 1 - k0);
                 const uint32_t ph = (uint32_t)(it & 1);
-                float m[NKT], l[NKT];
-#pragma unroll
+                float m0 = -1e30f, m1 = -1e30f, m2 = -1e30f, l0 = 0.f, l1 = 0.f, l2 = 0.f;
+                // The key-tile loop is NOT unrolled and masking is a separate compact pass: the first version of this loop
+                // (three unrolled key tiles x three code paths per piece) was ~60 KB of straight-line code, and ncu showed the
+                // warps waiting for instruction fetch ("no_instruction" the top stall, 17 % issue utilisation).
+#pragma unroll 1
                 for (int j = 0; j < NKT; ++j) {
                     const int a = max(lo - j * BKV, 0), b = min(hi - j * BKV, BKV - 1);    // visible columns of tile j: [a, b]
                     mbar_wait(bars.s(j), ph);
                     tc_fence_after();
                     uint32_t s[BKV];
-                    // 32-column pieces: 0 = no row of this warp sees it (not read), 2 = every row sees all of it (no
-                    // compares), 1 = mixed
+                    // 32-column pieces: 0 = no row of this warp sees it (not read), 2 = every row sees all of it, 1 = mixed
                     int kind[4];
 #pragma unroll
                     for (int pc = 0; pc < 4; ++pc) {
@@ -194,63 +196,55 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                         if (any) tc_ld_32x32b_x32(lane_addr + (uint32_t)(j * 128 + pc * 32), *reinterpret_cast<uint32_t(*)[32]>(&s[pc * 32]));
                     }
                     tc_wait_ld();
-                    float mx = -1e30f;
+                    // masked scores -> -inf (2^-inf = 0 below); pieces nobody sees are treated as -inf without being read
+                    constexpr uint32_t NEG_INF = 0xff800000u;
 #pragma unroll
                     for (int pc = 0; pc < 4; ++pc) {
-                        if (kind[pc] == 2) {
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(s[pc * 32 + c]));
-                        } else if (kind[pc] == 1) {
+                        if (kind[pc] == 1) {
 #pragma unroll
                             for (int c = 0; c < 32; ++c) {
                                 const int col = pc * 32 + c;
-                                if (col >= a && col <= b) mx = fmaxf(mx, __uint_as_float(s[col]));
+                                s[col] = (col >= a && col <= b) ? s[col] : NEG_INF;
                             }
+                        } else if (kind[pc] == 0) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) s[pc * 32 + c] = NEG_INF;
                         }
                     }
-                    m[j] = mx;
+                    float mx0 = -1e30f, mx1 = -1e30f, mx2 = -1e30f, mx3 = -1e30f;     // (finite floor: a fully masked row stays well defined)
+#pragma unroll
+                    for (int c = 0; c < BKV; c += 4) {
+                        mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+                        mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+                        mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+                    }
+                    const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                     const float mb = mx * scale_log2e;
-                    float sum = 0.f;
+                    float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {          // 64 scores -> 32 fp16 pairs -> P columns [32*half, +32)
                         uint32_t pk[32];
 #pragma unroll
-                        for (int pp = 0; pp < 2; ++pp) {
-                            const int pc = half * 2 + pp;
-                            if (kind[pc] == 2) {
-#pragma unroll
-                                for (int c2 = 0; c2 < 16; ++c2) {
-                                    const int col = pc * 32 + 2 * c2;
-                                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[col]), scale_log2e, -mb));
-                                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[col + 1]), scale_log2e, -mb));
-                                    sum += p0 + p1;
-                                    const __half2 h2 = __floats2half2_rn(p0, p1);
-                                    pk[pp * 16 + c2] = *reinterpret_cast<const uint32_t*>(&h2);
-                                }
-                            } else if (kind[pc] == 1) {
-#pragma unroll
-                                for (int c2 = 0; c2 < 16; ++c2) {
-                                    const int col = pc * 32 + 2 * c2;
-                                    float p0 = 0.f, p1 = 0.f;
-                                    if (col >= a && col <= b) p0 = ex2_approx(fmaf(__uint_as_float(s[col]), scale_log2e, -mb));
-                                    if (col + 1 >= a && col + 1 <= b) p1 = ex2_approx(fmaf(__uint_as_float(s[col + 1]), scale_log2e, -mb));
-                                    sum += p0 + p1;
-                                    const __half2 h2 = __floats2half2_rn(p0, p1);
-                                    pk[pp * 16 + c2] = *reinterpret_cast<const uint32_t*>(&h2);
-                                }
-                            } else {
-#pragma unroll
-                                for (int c2 = 0; c2 < 16; ++c2) pk[pp * 16 + c2] = 0u;
-                            }
+                        for (int c2 = 0; c2 < 32; ++c2) {
+                            const int col = half * 64 + 2 * c2;
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(s[col]), scale_log2e, -mb));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(s[col + 1]), scale_log2e, -mb));
+                            sum0 += p0;
+                            sum1 += p1;
+                            const __half2 h2 = __floats2half2_rn(p0, p1);
+                            pk[c2] = *reinterpret_cast<const uint32_t*>(&h2);
                         }
                         tc_st_32x32b_x32(lane_addr + (uint32_t)(j * 128 + half * 32), pk);
                     }
-                    l[j] = sum;
+                    const float sum = sum0 + sum1;
+                    if (j == 0) { m0 = mx; l0 = sum; } else if (j == 1) { m1 = mx; l1 = sum; } else { m2 = mx; l2 = sum; }
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bars.p(j));
                 }
+                const float m[NKT] = {m0, m1, m2}, l[NKT] = {l0, l1, l2};
                 // ===== epilogue: combine the three partial softmaxes of the row =====
                 const float M = fmaxf(fmaxf(m[0], m[1]), m[2]);
                 float f[NKT], L = 0.f;

@@ -376,6 +376,26 @@ class LstmCrfPlan:
             )
         return self._bufs[key]
 
+    def _plan_struct(self, b, N, L):
+        """`b200_lstm_crf_plan` for this geometry and buffer set (cached in the buffer dict)."""
+        if "struct" not in b:
+            p = native.LstmCrfPlanStruct()
+            p.n, p.l, p.t, p.tp = N, L, b["T"], b["Tp"]
+            p.c1, _, p.k1 = self.w1.shape
+            p.c2, _, p.k2 = self.w2.shape
+            p.act1, p.act2 = self.act1, self.act2
+            p.hidden, p.k3, p.s3, p.pad3, p.act3 = self.hidden, self.k3, self.s3, self.pad3, self.act3
+            p.n_lstm, p.n_scores, p.act_l, p.lo, p.hi = len(self.lstm), self.n_scores, self.act_l, self.lo, self.hi
+            ptr = lambda t: None if t is None else t.data_ptr()
+            p.w1, p.b1, p.w2, p.b2, p.w3, p.b3 = ptr(self.w1), ptr(self.b1), ptr(self.w2), ptr(self.b2), ptr(self.w3), ptr(self.b3)
+            p.wl, p.bl = ptr(self.wl), ptr(self.bl)
+            for i, layer in enumerate(self.lstm):
+                p.reverse[i] = int(layer["reverse"])
+                p.wih[i], p.bias[i], p.whh[i] = ptr(layer["wih"]), ptr(layer["bias"]), ptr(layer["whh"])
+            p.stem, p.ya, p.yb, p.gx, p.hx = (ptr(b[k]) for k in ("stem", "ya", "yb", "gx", "hx"))
+            b["struct"] = p
+        return b["struct"]
+
     def forward_tiles(self, x, out=None, gemm_impl=native.GEMM_AUTO, events=None, return_features=False, streams=False,
                       slot=0):
         """
@@ -435,6 +455,13 @@ class LstmCrfPlan:
 
         def gather(buf):            # [tile][T][48][H] -> [T][N][H]
             return buf.permute(1, 0, 2, 3).reshape(T, nt * TB, H)[:, :N].clone()
+
+        if not streams and events is None and not return_features and gemm_impl == native.GEMM_AUTO \
+                and len(self.lstm) <= native.MAX_LSTM_LAYERS and os.environ.get("B200_COARSE_FWD", "1") != "0":
+            # the whole encoder from ONE C-ABI call (b200_lstm_crf_fwd); the per-kernel path below runs the same launches
+            # one ctypes call at a time (used when per-kernel events or intermediate activations are wanted)
+            native.lstm_crf_fwd(self._plan_struct(b, N, L), x, out, stream=main)
+            return out
 
         with _StreamStage("conv_stem", events, main):
             native.conv_stem(x, self.w1, self.b1, self.act1, self.w2, self.b2, self.act2, b["stem"], Lp, self.pad3)

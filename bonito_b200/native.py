@@ -18,6 +18,23 @@ _lib = None
 ACT_NONE, ACT_SWISH, ACT_TANH, ACT_CLAMP, ACT_SCALE, ACT_SWIGLU = 0, 1, 2, 3, 4, 5
 GEMM_AUTO, GEMM_TCGEN05, GEMM_MMA_SYNC = 0, 1, 2
 
+MAX_LSTM_LAYERS = 8
+
+
+class LstmCrfPlanStruct(ctypes.Structure):
+    """`b200_lstm_crf_plan` of include/bonito_b200.h."""
+    _fields_ = [("n", c_int), ("l", c_int), ("t", c_int), ("tp", c_int),
+                ("c1", c_int), ("k1", c_int), ("act1", c_int), ("c2", c_int), ("k2", c_int), ("act2", c_int),
+                ("hidden", c_int), ("k3", c_int), ("s3", c_int), ("pad3", c_int), ("act3", c_int),
+                ("n_lstm", c_int), ("n_scores", c_int), ("act_l", c_int),
+                ("lo", c_float), ("hi", c_float),
+                ("reverse", c_int * MAX_LSTM_LAYERS),
+                ("w1", c_void_p), ("b1", c_void_p), ("w2", c_void_p), ("b2", c_void_p), ("w3", c_void_p), ("b3", c_void_p),
+                ("wl", c_void_p), ("bl", c_void_p),
+                ("wih", c_void_p * MAX_LSTM_LAYERS), ("bias", c_void_p * MAX_LSTM_LAYERS), ("whh", c_void_p * MAX_LSTM_LAYERS),
+                ("stem", c_void_p), ("ya", c_void_p), ("yb", c_void_p), ("gx", c_void_p), ("hx", c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/bonito_b200.h
 SIGNATURES = {
     "b200_version": (c_int, []),
@@ -49,6 +66,7 @@ SIGNATURES = {
     "b200_debug_exchange_bench": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "b200_lstm_crf_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_crf_beam_search": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_crf_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
@@ -284,3 +302,12 @@ def crf_beam_search(scores, state_len, blank_score, beam_width, beam_cut, qscale
                                       _ptr(qstring), _stream(stream))
     _check(rc, "b200_crf_beam_search")
     return moves, sequence, qstring
+
+
+def lstm_crf_fwd(plan_struct, x, scores, stream=None):
+    """Whole encoder forward from one C call (see b200_lstm_crf_fwd); `plan_struct`: a filled LstmCrfPlanStruct."""
+    lib = require()
+    with torch.cuda.device(scores.device):
+        rc = lib.b200_lstm_crf_fwd(ctypes.byref(plan_struct), _ptr(_f16(x, "x")), _ptr(scores), _stream(stream))
+    _check(rc, "b200_lstm_crf_fwd")
+    return scores

@@ -206,6 +206,36 @@ int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank
                     void* workspace, void* moves, void* sequence, void* qstring, void* stream);
 
 /*
+ * ---- coarse entry point: the whole LSTM-CRF encoder forward of one batch from one call ----
+ * conv stem -> strided convolution (GEMM) -> n_lstm x (input projection GEMM + persistent recurrent layer) ->
+ * LinearCRFEncoder GEMM (+Clamp), enqueued on `stream` (14 launches for the hac shape).  Replaces the module-tree walk of
+ * `Serial.forward` over the encoder of a bonito.crf model (bonito/nn.py:82-89, bonito/crf/model.py:150-162) -- the span
+ * `Model.use_koi` swaps for koi.lstm.update_graph plus the layers around it.  Tile-layout recurrent kernel only
+ * (b200_lstm_tile_chunks(hidden) > 0).  The plan holds DEVICE pointers to packed weights (layouts as documented for the
+ * fine-grained entry points above: conv weights in torch layout, w3 [H][k3*c2] with k = tap*c2 + cin, wih / bias in gx column
+ * order, whh in W_hh row order) and to caller-owned work buffers:
+ *   stem  (n*tp*s3*c2 + k3*c2) halves, the last k3*c2 zeroed       ya, yb  tiles*t*48*H halves, zero-filled once
+ *   gx    tiles*t*4H*48 halves, zero-filled once                    hx      b200_lstm_rec_tile_workspace_bytes(n) bytes
+ * with tiles = ceil(n / 48), t = frames, tp = padded frames per chunk (the stem buffer holds tp*s3 samples per chunk).
+ * x [n][l] fp16 -> scores [n][t][n_scores] fp16 (no blank column).
+ */
+#define B200_MAX_LSTM_LAYERS 8
+typedef struct b200_lstm_crf_plan {
+    int n, l, t, tp;
+    int c1, k1, act1, c2, k2, act2;          /* conv stem */
+    int hidden, k3, s3, pad3, act3;          /* strided convolution into the LSTM width */
+    int n_lstm, n_scores, act_l;
+    float lo, hi;                            /* clamp bounds (act_l = B200_ACT_CLAMP) */
+    int reverse[B200_MAX_LSTM_LAYERS];
+    const void *w1, *b1, *w2, *b2, *w3, *b3, *wl, *bl;
+    const void* wih[B200_MAX_LSTM_LAYERS];
+    const void* bias[B200_MAX_LSTM_LAYERS];
+    const void* whh[B200_MAX_LSTM_LAYERS];
+    void *stem, *ya, *yb, *gx, *hx;
+} b200_lstm_crf_plan;
+int b200_lstm_crf_fwd(const b200_lstm_crf_plan* plan, const void* x, void* scores, void* stream);
+
+/*
  * Beam-search decode with the argument meaning of koi.decode.beam_search (bonito/crf/basecall.py:36-40): beam_width entries
  * (1..32), candidates more than beam_cut (natural-log units) below the best are dropped.  koi itself is a closed binary with
  * no pinned outputs, so this is this library's own backward-guided prefix beam search (oracle: crf_oracle.beam_search_native);

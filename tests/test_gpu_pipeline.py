@@ -65,11 +65,14 @@ def test_tile_pipelined_forward_is_bit_identical(n, monkeypatch):
         a = plan.forward(x, tiled=False).clone()
         b = plan.forward(x, tiled=True).clone()
         c = plan.forward(x).clone()
+        monkeypatch.setenv("B200_COARSE_FWD", "0")       # the same launches one ctypes call at a time
+        f = plan.forward(x, tiled=False).clone()
         monkeypatch.setenv("B200_LSTM_TILE", "0")
         d = plan.forward(x, tiled=False).clone()
         e = plan.forward(x, tiled=True).clone()
     torch.cuda.synchronize()
-    assert torch.equal(a, b) and torch.equal(a, c)
+    assert torch.equal(a, b) and torch.equal(a, c)       # a, c: the whole encoder from one C call (b200_lstm_crf_fwd)
+    assert torch.equal(a, f)
     assert torch.equal(d, e) and torch.equal(a, d)
 
 
