@@ -8,11 +8,12 @@
 //     SWIZZLE_128B, out-of-range rows zero-filled): every key tile is loaded ONCE per (chunk, head) and used by three
 //     query tiles; the tile needed next is always in flight while the current one is processed; Q is double buffered;
 //   * S_j = Q K_j^T: 4 tcgen05.mma (M=128, N=128, K=16) per key tile, fp32 accumulators in TMEM columns [128j, 128j+128);
-//   * four softmax warps, one thread per query row (tcgen05.ld 32x32b: thread i of warp w owns TMEM lane 32w+i): each key
-//     tile is normalised on its OWN row maximum m_j -- the 128 scores of a row and tile live in registers between the
+//   * eight softmax warps, two per TMEM lane quarter (tcgen05.ld 32x32b: thread i of a warp owns lane 32 (warp % 4) + i = one
+//     query row; the two warps of a row split each key tile's 128 columns in halves and exchange their row maxima through
+//     shared memory): each key tile is normalised on its OWN row maximum m_j -- the scores live in registers between the
 //     maximum and the exponentials, so S is read from TMEM exactly once -- and P_j = 2^((s - m_j) * scale) is written back
 //     as fp16 pairs into the first 64 columns of S_j (tcgen05.st), i.e. as a TMEM-resident A operand.  32-column pieces
-//     that a whole warp sees unmasked take a compare-free path; pieces masked for the whole warp are not even read;
+//     that a whole warp sees unmasked skip the masking pass; pieces masked for the whole warp are not even read;
 //   * O_j = P_j V_j: 8 tcgen05.mma (M=128, N=64, K=16) per key tile with A from TMEM and B = V_j straight from its TMA
 //     layout (rows = keys = K, 128-byte rows of 64 head dims: the MN-major SWIZZLE_128B operand, "transpose B" bit of the
 //     instruction descriptor), accumulated into the LAST 64 columns of S_j; PV_j runs while the softmax warps work on j+1;
@@ -28,10 +29,12 @@
 namespace {
 
 constexpr int BQ = 128, BKV = 128, HD = 64, NKT = 3, RING = 4;
-constexpr int THREADS = 160;                       // 4 softmax warps + 1 TMA / MMA warp
+constexpr int SM_WARPS = 8;                        // softmax warps: two per TMEM lane quarter, each takes half of the columns
+constexpr int THREADS = (SM_WARPS + 1) * 32;       // + 1 TMA / MMA warp
 constexpr uint32_t TILE_BYTES = BQ * HD * 2;       // 16 KB: one 128 x 64 fp16 tile (128-byte rows)
 constexpr uint32_t OFF_Q = 0, OFF_K = 2 * TILE_BYTES, OFF_V = OFF_K + RING * TILE_BYTES, OFF_BARS = OFF_V + RING * TILE_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_BARS + 256 + 1024;   // ~162 KB
+constexpr uint32_t OFF_XCH = OFF_BARS + 256;       // float [4][2][BQ]: per-row maxima / sums exchanged between the two warps of a row
+constexpr uint32_t SMEM_BYTES = OFF_XCH + 4 * 2 * BQ * 4 + 1024;   // ~166 KB
 constexpr uint32_t TMEM_COLS = 512;                // S_j | P_j | O_j share columns [128j, 128j+128), j < 3
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -71,19 +74,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
         for (int sl = 0; sl < RING; ++sl) mbar_init(bars.kvfull(sl), 1);
         for (int j = 0; j < NKT; ++j) {
             mbar_init(bars.s(j), 1);
-            mbar_init(bars.p(j), 4);               // one arrive per softmax warp
+            mbar_init(bars.p(j), SM_WARPS);        // one arrive per softmax warp
         }
         mbar_init(bars.o(), 1);
-        mbar_init(bars.tfree(), 4);
+        mbar_init(bars.tfree(), SM_WARPS);
         mbar_fence_init();
     }
-    if (warp == 4) tc_alloc(tmem_slot, TMEM_COLS);
+    if (warp == SM_WARPS) tc_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 112);
 
-    if (warp == 4) {
+    if (warp == SM_WARPS) {
         // ===== TMA producer + MMA issuer (one thread) =====
         if (elect_one_sync()) {
             constexpr uint32_t idesc_s = tc_idesc_f16(BQ, BKV);
@@ -165,9 +168,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
         }
         __syncwarp();
     } else {
-        // ===== softmax warps: thread = query row =====
-        const int r = warp * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        // ===== softmax warps: a query row is shared by the two warps of its TMEM lane quarter (warp % 4): warp `hf` = warp / 4
+        // takes columns [64 hf, 64 hf + 64) of every key tile.  One warp per SM sub-partition left the kernel latency
+        // bound (IPC 0.14 in ncu); two interleave their tcgen05.ld / MUFU / tcgen05.st chains. =====
+        const int quarter = warp & 3, hf = warp >> 2;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* xch = reinterpret_cast<float*>(gbase + OFF_XCH);      // [slot 0..3][hf][row]
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quarter) : "memory"); };
         int it = 0;
         for (int item = blockIdx.x; item < items; item += (int)gridDim.x) {
             const int n = item / NH, h = item % NH;
@@ -176,30 +184,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                 // visible band of this row in band columns c = key - k0 (0 .. 383)
                 const int lo = max(BKV + r - wl, -k0), hi = min(BKV + r + wr, T - 1 - k0);
                 const uint32_t ph = (uint32_t)(it & 1);
-                float m0 = -1e30f, m1 = -1e30f, m2 = -1e30f, l0 = 0.f, l1 = 0.f, l2 = 0.f;
-                // The key-tile loop is NOT unrolled and masking is a separate compact pass: the first version of this loop
-                // (three unrolled key tiles x three code paths per piece) was ~60 KB of straight-line code, and ncu showed the
-                // warps waiting for instruction fetch ("no_instruction" the top stall, 17 % issue utilisation).
+                float m0 = -1e30f, m1 = -1e30f, m2 = -1e30f, l0 = 0.f, l1 = 0.f, l2 = 0.f;   // m: row maxima; l: THIS warp's partial sums
 #pragma unroll 1
                 for (int j = 0; j < NKT; ++j) {
-                    const int a = max(lo - j * BKV, 0), b = min(hi - j * BKV, BKV - 1);    // visible columns of tile j: [a, b]
+                    // visible columns of this warp's half of tile j, relative to the half: [a, b] within 0..63
+                    const int a = max(lo - j * BKV - hf * 64, 0), b = min(hi - j * BKV - hf * 64, 63);
                     mbar_wait(bars.s(j), ph);
                     tc_fence_after();
-                    uint32_t s[BKV];
-                    // 32-column pieces: 0 = no row of this warp sees it (not read), 2 = every row sees all of it, 1 = mixed
-                    int kind[4];
+                    uint32_t s[64];
+                    int kind[2];     // per 32-column piece: 0 = nobody in the warp sees it (not read), 2 = everybody sees all of it, 1 = mixed
 #pragma unroll
-                    for (int pc = 0; pc < 4; ++pc) {
+                    for (int pc = 0; pc < 2; ++pc) {
                         const bool any = __any_sync(0xffffffffu, a <= pc * 32 + 31 && b >= pc * 32);
                         const bool all = __all_sync(0xffffffffu, a <= pc * 32 && b >= pc * 32 + 31);
                         kind[pc] = all ? 2 : (any ? 1 : 0);
-                        if (any) tc_ld_32x32b_x32(lane_addr + (uint32_t)(j * 128 + pc * 32), *reinterpret_cast<uint32_t(*)[32]>(&s[pc * 32]));
+                        if (any) tc_ld_32x32b_x32(lane_addr + (uint32_t)(j * 128 + hf * 64 + pc * 32), *reinterpret_cast<uint32_t(*)[32]>(&s[pc * 32]));
                     }
                     tc_wait_ld();
-                    // masked scores -> -inf (2^-inf = 0 below); pieces nobody sees are treated as -inf without being read
-                    constexpr uint32_t NEG_INF = 0xff800000u;
+                    constexpr uint32_t NEG_INF = 0xff800000u;     // masked scores -> -inf (2^-inf = 0 below)
 #pragma unroll
-                    for (int pc = 0; pc < 4; ++pc) {
+                    for (int pc = 0; pc < 2; ++pc) {
                         if (kind[pc] == 1) {
 #pragma unroll
                             for (int c = 0; c < 32; ++c) {
@@ -213,30 +217,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                     }
                     float mx0 = -1e30f, mx1 = -1e30f, mx2 = -1e30f, mx3 = -1e30f;     // (finite floor: a fully masked row stays well defined)
 #pragma unroll
-                    for (int c = 0; c < BKV; c += 4) {
+                    for (int c = 0; c < 64; c += 4) {
                         mx0 = fmaxf(mx0, __uint_as_float(s[c]));
                         mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
                         mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
                         mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
                     }
-                    const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                    float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                    // row maximum over both halves: exchange through shared memory with the partner warp
+                    xch[((j & 1) * 2 + hf) * BQ + r] = mx;
+                    pair_sync();
+                    mx = fmaxf(mx, xch[((j & 1) * 2 + (hf ^ 1)) * BQ + r]);
                     const float mb = mx * scale_log2e;
                     float sum0 = 0.f, sum1 = 0.f;
+                    uint32_t pk[32];
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {          // 64 scores -> 32 fp16 pairs -> P columns [32*half, +32)
-                        uint32_t pk[32];
-#pragma unroll
-                        for (int c2 = 0; c2 < 32; ++c2) {
-                            const int col = half * 64 + 2 * c2;
-                            const float p0 = ex2_approx(fmaf(__uint_as_float(s[col]), scale_log2e, -mb));
-                            const float p1 = ex2_approx(fmaf(__uint_as_float(s[col + 1]), scale_log2e, -mb));
-                            sum0 += p0;
-                            sum1 += p1;
-                            const __half2 h2 = __floats2half2_rn(p0, p1);
-                            pk[c2] = *reinterpret_cast<const uint32_t*>(&h2);
-                        }
-                        tc_st_32x32b_x32(lane_addr + (uint32_t)(j * 128 + half * 32), pk);
+                    for (int c2 = 0; c2 < 32; ++c2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * c2]), scale_log2e, -mb));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * c2 + 1]), scale_log2e, -mb));
+                        sum0 += p0;
+                        sum1 += p1;
+                        const __half2 h2 = __floats2half2_rn(p0, p1);
+                        pk[c2] = *reinterpret_cast<const uint32_t*>(&h2);
                     }
+                    tc_st_32x32b_x32(lane_addr + (uint32_t)(j * 128 + hf * 32), pk);   // P columns of keys 64 hf .. 64 hf + 63
                     const float sum = sum0 + sum1;
                     if (j == 0) { m0 = mx; l0 = sum; } else if (j == 1) { m1 = mx; l1 = sum; } else { m2 = mx; l2 = sum; }
                     tc_wait_st();
@@ -244,33 +248,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bars.p(j));
                 }
-                const float m[NKT] = {m0, m1, m2}, l[NKT] = {l0, l1, l2};
-                // ===== epilogue: combine the three partial softmaxes of the row =====
-                const float M = fmaxf(fmaxf(m[0], m[1]), m[2]);
-                float f[NKT], L = 0.f;
-#pragma unroll
-                for (int j = 0; j < NKT; ++j) {
-                    f[j] = ex2_approx(fmaxf((m[j] - M) * scale_log2e, -126.f));
-                    if (m[j] <= -1e30f) f[j] = 0.f;
-                    L = fmaf(l[j], f[j], L);
-                }
+                // ===== epilogue: combine the three partial softmaxes of the row; this warp writes head dims [32 hf, 32 hf + 32) =====
+                const float M = fmaxf(fmaxf(m0, m1), m2);
+                float f0 = m0 <= -1e30f ? 0.f : ex2_approx(fmaxf((m0 - M) * scale_log2e, -126.f));
+                float f1 = m1 <= -1e30f ? 0.f : ex2_approx(fmaxf((m1 - M) * scale_log2e, -126.f));
+                float f2 = m2 <= -1e30f ? 0.f : ex2_approx(fmaxf((m2 - M) * scale_log2e, -126.f));
+                const float Lpart = fmaf(l0, f0, fmaf(l1, f1, l2 * f2));
+                xch[(2 * 2 + hf) * BQ + r] = Lpart;         // slots 2: the partner's share of the denominator
+                pair_sync();
+                const float L = Lpart + xch[(2 * 2 + (hf ^ 1)) * BQ + r];
                 const float inv = L > 0.f ? 1.0f / L : 0.f;
-                f[0] *= inv; f[1] *= inv; f[2] *= inv;
+                f0 *= inv; f1 *= inv; f2 *= inv;
                 mbar_wait(bars.o(), ph);
                 tc_fence_after();
-                __half* dst = out + ((size_t)n * T + q) * (size_t)(NH * HD) + h * HD;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                __half* dst = out + ((size_t)n * T + q) * (size_t)(NH * HD) + h * HD + hf * 32;
+                {
                     uint32_t o0[32], o1[32], o2[32];
-                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(0 * 128 + 64 + half * 32), o0);
-                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(1 * 128 + 64 + half * 32), o1);
-                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(2 * 128 + 64 + half * 32), o2);
+                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(0 * 128 + 64 + hf * 32), o0);
+                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(1 * 128 + 64 + hf * 32), o1);
+                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(2 * 128 + 64 + hf * 32), o2);
                     tc_wait_ld();
-                    if (half == 1) {            // all of this tile's TMEM has been read: the next tile's MMAs may overwrite it
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bars.tfree());
-                    }
+                    // all of this tile's TMEM has been read by this warp: the next tile's MMAs may overwrite it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars.tfree());
                     if (q < T) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -278,11 +279,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
 #pragma unroll
                             for (int p = 0; p < 4; ++p) {
                                 const int c = g * 8 + 2 * p;
-                                const float v0 = __uint_as_float(o0[c]) * f[0] + __uint_as_float(o1[c]) * f[1] + __uint_as_float(o2[c]) * f[2];
-                                const float v1 = __uint_as_float(o0[c + 1]) * f[0] + __uint_as_float(o1[c + 1]) * f[1] + __uint_as_float(o2[c + 1]) * f[2];
+                                const float v0 = __uint_as_float(o0[c]) * f0 + __uint_as_float(o1[c]) * f1 + __uint_as_float(o2[c]) * f2;
+                                const float v1 = __uint_as_float(o0[c + 1]) * f0 + __uint_as_float(o1[c + 1]) * f1 + __uint_as_float(o2[c + 1]) * f2;
                                 hh[p] = __floats2half2_rn(v0, v1);
                             }
-                            *reinterpret_cast<uint4*>(dst + half * 32 + g * 8) = *reinterpret_cast<const uint4*>(hh);
+                            *reinterpret_cast<uint4*>(dst + g * 8) = *reinterpret_cast<const uint4*>(hh);
                         }
                     }
                 }
@@ -292,7 +293,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tc_dealloc(tmem_base, TMEM_COLS);
+    if (warp == SM_WARPS) tc_dealloc(tmem_base, TMEM_COLS);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

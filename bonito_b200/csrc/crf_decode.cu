@@ -47,7 +47,10 @@ struct DecodeSmem {
     static constexpr size_t kUnionBytes = (2 * 4 * S * sizeof(float) > (size_t)TB * S) ? 2 * 4 * S * sizeof(float) : (size_t)TB * S;
     static constexpr size_t kPart = kUnion + kUnionBytes;              // float [2][NW][4]
     static constexpr size_t kKt = kPart + 2 * NW * 4 * sizeof(float);  // float [2]: per-step posterior normaliser
-    static constexpr size_t kRed = kKt + 16;
+    static constexpr int PF = 4;                                       // prefetch depth (steps) of the cp.async rings
+    static constexpr size_t kScRing = kKt + 16;                        // uint2 [PF][S]: score rows in flight
+    static constexpr size_t kBetaRing = kScRing + PF * S * sizeof(uint2);   // float [PF][S]: beta' rows in flight (pass 2)
+    static constexpr size_t kRed = kBetaRing + PF * S * sizeof(float);
     static constexpr size_t kRedI = kRed + NW * sizeof(float);
     static constexpr size_t kOut = kRedI + NW * sizeof(int) + 16;      // u8 [3][T]
     static size_t bytes(int T) { return kOut + 3 * (size_t)T + 16; }
@@ -55,6 +58,16 @@ struct DecodeSmem {
 
 template <int V>
 struct IntC { static constexpr int value = V; };
+
+// 8- / 4-byte asynchronous copies global -> shared (LDGSTS): the per-step score and beta' rows are fetched PF steps ahead
+// into shared-memory rings; every thread reads back only the element it copied itself, so its own wait_group is enough.
+// (With a one-step register prefetch the global-load latency was the top stall of this kernel next to the per-step barrier.)
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+}
 
 // All recurrences run in the log2 domain (scores are multiplied by log2(e) once when they are loaded): every
 // exponential / logarithm is then a single bare MUFU instruction.  (The first version of this kernel used __expf / __logf
@@ -76,6 +89,9 @@ crf_decode_kernel(const __half* __restrict__ scores, int T, float blank, float q
     uint8_t (*bp_blk)[S] = reinterpret_cast<uint8_t (*)[S]>(sm + L::kUnion);
     float (*part)[NW][4] = reinterpret_cast<float (*)[NW][4]>(sm + L::kPart);
     float* kt_sh = reinterpret_cast<float*>(sm + L::kKt);
+    constexpr int PF = L::PF;
+    uint2 (*sc_ring)[S] = reinterpret_cast<uint2 (*)[S]>(sm + L::kScRing);
+    float (*beta_ring)[S] = reinterpret_cast<float (*)[S]>(sm + L::kBetaRing);
     float* red = reinterpret_cast<float*>(sm + L::kRed);
     int* red_i = reinterpret_cast<int*>(sm + L::kRedI);
     uint8_t* out_sh = sm + L::kOut;
@@ -107,17 +123,24 @@ crf_decode_kernel(const __half* __restrict__ scores, int T, float blank, float q
             dst[2 * S + s] = m23.x * LOG2E; dst[3 * S + s] = m23.y * LOG2E;
         };
         scatter(msh[0], sc[(size_t)(T - 1) * S]);
-        uint2 raw_next = (T > 1) ? sc[(size_t)(T - 2) * S] : make_uint2(0, 0);
-        const uint2* sc_pf = sc + (size_t)(T - 3) * S;        // next prefetch: row t-2 of the step being processed
+        // score rows T-2, T-3, ... travel through the ring: row r lives in slot r % PF; PF-1 groups are kept in flight
+        for (int r = T - 2; r > T - 2 - (PF - 1); --r) {
+            if (r >= 0) cp_async_8(&sc_ring[r & (PF - 1)][s], sc + (size_t)r * S);
+            cp_async_commit();
+        }
         float* beta_p = beta + (size_t)(T - 1) * S + s;
         double* bsum_p = bsum + (T - 1);
         double acc_shift = 0.0;
         __syncthreads();
         auto bwd = [&](int t, auto cur_c) {
             constexpr int CUR = decltype(cur_c)::value;
-            if (t > 0) scatter(msh[CUR ^ 1], raw_next);
-            if (t > 1) raw_next = *sc_pf;
-            sc_pf -= S;
+            {   // next row into the ring (row t-PF; its slot held row t, scattered in the previous step), then wait for row t-1
+                const int r = t - PF;
+                if (r >= 0) cp_async_8(&sc_ring[r & (PF - 1)][s], sc + (size_t)r * S);
+                cp_async_commit();
+                cp_async_wait<PF - 1>();
+            }
+            if (t > 0) scatter(msh[CUR ^ 1], sc_ring[(t - 1) & (PF - 1)][s]);
             const float b0 = buf[CUR][0];
             const float4 mv = *reinterpret_cast<const float4*>(&msh[CUR][4 * s]);
             const float4 bs = *reinterpret_cast<const float4*>(&buf[CUR][4 * (s % Q)]);
@@ -172,25 +195,35 @@ crf_decode_kernel(const __half* __restrict__ scores, int T, float blank, float q
         double asum = 0.0;     // thread 0: sum of the alpha' re-centring shifts before step t
         if (s == 0) kt_sh[0] = (float)(bsum[1] - logz);       // step 0: alpha'_0 = 0, asum = 0
         __syncthreads();
-        uint2 mraw = sc[0];
-        float bnext = beta[(size_t)1 * S + s];
+        cp_async_wait<0>();
+        // score row t and beta' row t+1 of step t live in slot t % PF of the rings; PF-1 steps are kept in flight
+        for (int r = 0; r < PF - 1; ++r) {
+            if (r < T) {
+                cp_async_8(&sc_ring[r][s], sc + (size_t)r * S);
+                cp_async_4(&beta_ring[r][s], beta + (size_t)(r + 1) * S + s);
+            }
+            cp_async_commit();
+        }
         double bs_next2 = (T > 1 && s == 0) ? bsum[2] : 0.0;   // thread 0: bsum[t+2], for the normaliser of step t+1
-        const uint2* sc_p = sc + S;                           // row t+1
-        const float* beta_p = beta + (size_t)2 * S + s;       // row t+2
         const double* bsum_p = bsum + 3;
         uint8_t* bp_p = bp + s;
         float* pm_p = pm + s;                                 // used by threads 0..3
         auto fwd = [&](int t, auto cur_c) {
             constexpr int CUR = decltype(cur_c)::value;
-            uint2 mraw_n = make_uint2(0, 0);
-            float bn_n = 0.f;
             double bs_n = 0.0;
-            if (t + 1 < T) {  // prefetch: none of this depends on the recurrence
-                mraw_n = *sc_p;
-                bn_n = *beta_p;
-                if (s == 0 && t + 2 < T) bs_n = *bsum_p;
+            {
+                const int r = t + PF - 1;
+                if (r < T) {
+                    cp_async_8(&sc_ring[r & (PF - 1)][s], sc + (size_t)r * S);
+                    cp_async_4(&beta_ring[r & (PF - 1)][s], beta + (size_t)(r + 1) * S + s);
+                }
+                cp_async_commit();
+                if (s == 0 && t + 3 <= T) bs_n = *bsum_p;
+                cp_async_wait<PF - 1>();
             }
-            sc_p += S; beta_p += S; ++bsum_p;
+            ++bsum_p;
+            const uint2 mraw = sc_ring[t & (PF - 1)][s];
+            const float bnext = beta_ring[t & (PF - 1)][s];
             const float2 m01 = __half22float2(*reinterpret_cast<const __half2*>(&mraw.x));
             const float2 m23 = __half22float2(*reinterpret_cast<const __half2*>(&mraw.y));
             const float2 a0v0 = av[CUR][0];
@@ -236,7 +269,6 @@ crf_decode_kernel(const __half* __restrict__ scores, int T, float blank, float q
             mass += __shfl_xor_sync(0xffffffffu, mass, 8);
             mass += __shfl_xor_sync(0xffffffffu, mass, 16);
             if (lane < 4) part[CUR][warp][lane] = mass;
-            mraw = mraw_n; bnext = bn_n;
             __syncthreads();
             if (s < 4) {
                 float tot = 0.f;
