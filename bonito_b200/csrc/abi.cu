@@ -46,6 +46,8 @@ int launch_crf_beam_search(const __half* scores, int N, int T, int state_len, fl
 
 int launch_lstm_crf_fwd(const b200_lstm_crf_plan* p, const __half* x, __half* scores, cudaStream_t stream);
 
+int copy_attention_timeline(long long* host_out, int max_tiles);
+
 static thread_local char g_err[1024] = "";
 
 void b200_set_error(const char* fmt, ...) {
@@ -184,6 +186,11 @@ int b200_lstm_rec_tile_fwd(const void* gx, const void* whh, void* y, void* works
 int b200_debug_lstm_tile_timeline(long long* host_out, int max_steps) {
     B200_REQUIRE(host_out != nullptr && max_steps > 0, "lstm_tile_timeline: bad arguments");
     return copy_lstm_timeline6(host_out, max_steps);
+}
+
+int b200_debug_attention_timeline(long long* host_out, int max_tiles) {
+    B200_REQUIRE(host_out != nullptr && max_tiles > 0, "attention_timeline: bad arguments");
+    return copy_attention_timeline(host_out, max_tiles);
 }
 
 int b200_debug_tmem_probe(void* out, void* stream) {

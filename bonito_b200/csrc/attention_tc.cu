@@ -44,6 +44,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// timeline of CTA 0 (B200_ATTN_DEBUG=1): per query tile, SM-clock stamps of
+//   MMA thread: [0] Q ready + TMEM free  [1] QK MMAs issued  [2] PV MMAs issued (all p(j) seen)  [3] O committed + complete  [4] loads issued
+//   softmax warp 0: [5] s(0) seen [6] S_0 loaded [7] max exchanged [8] P_0 stored + arrived [9] s(1) seen [10] P_1 arrived
+//                   [11] P_2 arrived [12] o seen [13] O loaded [14] output stored
+constexpr int ATL_TILES = 64;
+__device__ long long g_attn_timeline[ATL_TILES][16];
+
 struct AttnBars {
     uint32_t base;
     __device__ __forceinline__ uint32_t qfull(int b) const { return base + 8u * (uint32_t)b; }              // 2
@@ -56,7 +63,7 @@ struct AttnBars {
 
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restrict__ out, int N, int T, int NH, int wl,
-                    int wr, float scale_log2e) {
+                    int wr, float scale_log2e, int debug) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-B alignment
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -67,6 +74,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nqt = (T + BQ - 1) / BQ;             // query tiles per (chunk, head); key tiles -1 .. nqt are loaded
     const int items = N * NH;
+    const bool tl = debug != 0 && blockIdx.x == 0;
+#define ATL(it_, k_) do { if (tl && (it_) < ATL_TILES) g_attn_timeline[(it_)][(k_)] = clock64(); } while (0)
 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_qkv));
@@ -130,6 +139,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                     mbar_wait(bars.qfull(it & 1), (uint32_t)((it >> 1) & 1));
                     if (it > 0) mbar_wait(bars.tfree(), (uint32_t)((it - 1) & 1));    // the previous tile's O has been read
                     tc_fence_after();
+                    ATL(it, 0);
                     const uint64_t qdesc = tc_smem_desc_sw128(base + OFF_Q + (it & 1) * TILE_BYTES);
 #pragma unroll
                     for (int j = 0; j < NKT; ++j) {
@@ -142,6 +152,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                             tc_mma_ss(tmem_base + (uint32_t)(j * 128), qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
                         tc_commit(bars.s(j));
                     }
+                    ATL(it, 1);
                     // O_j = P_j V_j  (A = P_j from TMEM: lane = query, column c = keys 2c, 2c+1; B = V_j MN-major: K = keys are
                     // the 128-byte rows, 8 keys per 1024-byte swizzle atom: one K = 16 step advances the descriptor by 2048 B)
 #pragma unroll
@@ -156,13 +167,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                                       vdesc + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0 ? 1u : 0u);
                     }
                     tc_commit(bars.o());
+                    ATL(it, 2);
                     // once these MMAs have completed, key tile qt-1 of the item (and, after the last query tile, the rest)
                     // is dead: refill its ring slot with the key tile four ahead, and fetch the Q after next
                     mbar_wait(bars.o(), (uint32_t)(it & 1));
+                    ATL(it, 3);
                     kl_released = first_kl + (qt + 1 < nqt ? qt + 1 : nqt + 2);
                     ++it;
                     issue_loads();
                     --it;
+                    ATL(it, 4);
                 }
             }
         }
@@ -191,6 +205,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                     const int a = max(lo - j * BKV - hf * 64, 0), b = min(hi - j * BKV - hf * 64, 63);
                     mbar_wait(bars.s(j), ph);
                     tc_fence_after();
+                    if (warp == 0 && lane == 0) { if (j == 0) ATL(it, 5); else if (j == 1) ATL(it, 9); }
                     uint32_t s[64];
                     int kind[2];     // per 32-column piece: 0 = nobody in the warp sees it (not read), 2 = everybody sees all of it, 1 = mixed
 #pragma unroll
@@ -201,6 +216,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                         if (any) tc_ld_32x32b_x32(lane_addr + (uint32_t)(j * 128 + hf * 64 + pc * 32), *reinterpret_cast<uint32_t(*)[32]>(&s[pc * 32]));
                     }
                     tc_wait_ld();
+                    if (warp == 0 && lane == 0 && j == 0) ATL(it, 6);
                     constexpr uint32_t NEG_INF = 0xff800000u;     // masked scores -> -inf (2^-inf = 0 below)
 #pragma unroll
                     for (int pc = 0; pc < 2; ++pc) {
@@ -228,6 +244,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                     xch[((j & 1) * 2 + hf) * BQ + r] = mx;
                     pair_sync();
                     mx = fmaxf(mx, xch[((j & 1) * 2 + (hf ^ 1)) * BQ + r]);
+                    if (warp == 0 && lane == 0 && j == 0) ATL(it, 7);
                     const float mb = mx * scale_log2e;
                     float sum0 = 0.f, sum1 = 0.f;
                     uint32_t pk[32];
@@ -247,6 +264,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bars.p(j));
+                    if (warp == 0 && lane == 0) { if (j == 0) ATL(it, 8); else if (j == 1) ATL(it, 10); else ATL(it, 11); }
                 }
                 // ===== epilogue: combine the three partial softmaxes of the row; this warp writes head dims [32 hf, 32 hf + 32) =====
                 const float M = fmaxf(fmaxf(m0, m1), m2);
@@ -261,6 +279,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                 f0 *= inv; f1 *= inv; f2 *= inv;
                 mbar_wait(bars.o(), ph);
                 tc_fence_after();
+                if (warp == 0 && lane == 0) ATL(it, 12);
                 __half* dst = out + ((size_t)n * T + q) * (size_t)(NH * HD) + h * HD + hf * 32;
                 {
                     uint32_t o0[32], o1[32], o2[32];
@@ -272,6 +291,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bars.tfree());
+                    if (warp == 0 && lane == 0) ATL(it, 13);
                     if (q < T) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -286,10 +306,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                             *reinterpret_cast<uint4*>(dst + g * 8) = *reinterpret_cast<const uint4*>(hh);
                         }
                     }
+                    if (warp == 0 && lane == 0) ATL(it, 14);
                 }
             }
         }
     }
+#undef ATL
 
     tc_fence_before();
     __syncthreads();
@@ -339,7 +361,15 @@ int launch_attention_tc(const __half* qkv, __half* out, int N, int T, int NH, in
     const int items = N * NH;
     const int grid = items < sms ? items : sms;
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
-    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map, out, N, T, NH, wl, wr, scale_log2e);
+    const char* dbg = getenv("B200_ATTN_DEBUG");
+    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map, out, N, T, NH, wl, wr, scale_log2e, dbg ? atoi(dbg) : 0);
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+int copy_attention_timeline(long long* host_out, int max_tiles) {
+    const int n = max_tiles < ATL_TILES ? max_tiles : ATL_TILES;
+    B200_CHECK_CUDA(cudaDeviceSynchronize());
+    B200_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_attn_timeline, sizeof(long long) * 16 * n));
+    return n;
 }

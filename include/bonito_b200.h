@@ -127,6 +127,10 @@ size_t b200_lstm_rec_tile_workspace_bytes(int n);
 int b200_lstm_rec_tile_fwd(const void* gx, const void* whh, void* y, void* workspace, int t, int n, int hidden,
                            int reverse, void* stream);
 
+/* Timing aid: after a b200_attention_fwd launched with B200_ATTN_DEBUG=1, the SM-clock stamps CTA 0 recorded for its first
+ * query tiles ([tile][16] int64, HOST buffer; see attention_tc.cu).  Returns the number of tiles copied (<= 64). */
+int b200_debug_attention_timeline(long long* host_out, int max_tiles);
+
 /* Timing aid: as b200_debug_lstm_timeline, for b200_lstm_rec_tile_fwd. */
 int b200_debug_lstm_tile_timeline(long long* host_out, int max_steps);
 

@@ -152,7 +152,7 @@ def test_lstm_tile_kernel_matches_oracle(native, n, t, reverse):
     partial and multiple tiles, 1..3 active sub-tiles, T below / above the ring depth, both directions."""
     H = 384
     tb, cs = native.lstm_tile_chunks(H), native.lstm_tile_cluster(H)
-    assert (tb, cs) == (48, 6)
+    assert (tb, cs) in ((48, 6), (64, 6))       # B200_LSTM_SHAPE=3x16 (default) / 2x32
     cw = 4 * H // cs
     nt = -(-n // tb)
     g = torch.Generator().manual_seed(1000 + n + t)
