@@ -249,13 +249,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                     float sum0 = 0.f, sum1 = 0.f;
                     uint32_t pk[32];
 #pragma unroll
-                    for (int c2 = 0; c2 < 32; ++c2) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * c2]), scale_log2e, -mb));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * c2 + 1]), scale_log2e, -mb));
-                        sum0 += p0;
-                        sum1 += p1;
-                        const __half2 h2 = __floats2half2_rn(p0, p1);
-                        pk[c2] = *reinterpret_cast<const uint32_t*>(&h2);
+                    for (int pc = 0; pc < 2; ++pc) {
+                        if (kind[pc] != 0) {          // (warp-uniform) a piece nobody sees costs no exponentials: P = 0
+#pragma unroll
+                            for (int c2 = 0; c2 < 16; ++c2) {
+                                const float p0 = ex2_approx(fmaf(__uint_as_float(s[pc * 32 + 2 * c2]), scale_log2e, -mb));
+                                const float p1 = ex2_approx(fmaf(__uint_as_float(s[pc * 32 + 2 * c2 + 1]), scale_log2e, -mb));
+                                sum0 += p0;
+                                sum1 += p1;
+                                const __half2 h2 = __floats2half2_rn(p0, p1);
+                                pk[pc * 16 + c2] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                        } else {
+#pragma unroll
+                            for (int c2 = 0; c2 < 16; ++c2) pk[pc * 16 + c2] = 0u;
+                        }
                     }
                     tc_st_32x32b_x32(lane_addr + (uint32_t)(j * 128 + hf * 32), pk);   // P columns of keys 64 hf .. 64 hf + 63
                     const float sum = sum0 + sum1;
