@@ -378,7 +378,9 @@ def bench_sup(ctx, peaks, model, spec, L, steps, warmup, with_e2e=True):
         return _decoder(scores, spec["state_len"], blank_score=plan.blank_score, qscale=qs["scale"], qbias=qs["bias"],
                         events=events, slot=slot)
 
-    elapsed_ms, events, enqueue_ms = time_resident(ctx, step, steps, warmup, slots=N_SLOTS)
+    # one batch at a time: the sup step is one long chain of chip-filling GEMMs, a second batch in flight buys nothing
+    # (54.5 vs 56.2 ms measured) and would blur the per-kernel event times
+    elapsed_ms, events, enqueue_ms = time_resident(ctx, step, steps, warmup, slots=1)
     e2e_ms = time_e2e(ctx, model, host_batch, steps, qs) if with_e2e else 0.0
     elapsed_ms, e2e_ms = ctx.max_over_ranks([elapsed_ms, e2e_ms])
     log(f"sup L={L}: resident {elapsed_ms / steps:.2f} ms/step" + (f", e2e {e2e_ms / steps:.2f}" if with_e2e else ""))

@@ -253,12 +253,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
                         if (kind[pc] != 0) {          // (warp-uniform) a piece nobody sees costs no exponentials: P = 0
 #pragma unroll
                             for (int c2 = 0; c2 < 16; ++c2) {
-                                const float p0 = ex2_approx(fmaf(__uint_as_float(s[pc * 32 + 2 * c2]), scale_log2e, -mb));
-                                const float p1 = ex2_approx(fmaf(__uint_as_float(s[pc * 32 + 2 * c2 + 1]), scale_log2e, -mb));
-                                sum0 += p0;
-                                sum1 += p1;
-                                const __half2 h2 = __floats2half2_rn(p0, p1);
-                                pk[pc * 16 + c2] = *reinterpret_cast<const uint32_t*>(&h2);
+                                // two exponentials per MUFU operation: the arguments (<= 0) are rounded to fp16 -- P is stored
+                                // as fp16 anyway -- and ex2.approx.f16x2 returns the packed pair the A operand wants; the row
+                                // sum is taken over the ROUNDED probabilities, i.e. over exactly what the tensor core multiplies
+                                const __half2 x2 = __floats2half2_rn(fmaf(__uint_as_float(s[pc * 32 + 2 * c2]), scale_log2e, -mb),
+                                                                     fmaf(__uint_as_float(s[pc * 32 + 2 * c2 + 1]), scale_log2e, -mb));
+                                uint32_t pbits;
+                                asm("ex2.approx.f16x2 %0, %1;" : "=r"(pbits) : "r"(*reinterpret_cast<const uint32_t*>(&x2)));
+                                const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pbits));
+                                sum0 += pf.x;
+                                sum1 += pf.y;
+                                pk[pc * 16 + c2] = pbits;
                             }
                         } else {
 #pragma unroll
