@@ -139,7 +139,7 @@ class SeqdistModel(Module):
             if find_transformer_encoder(self.encoder) is not None:
                 self._plan = compile_transformer(self.encoder, device)
             else:
-                self._plan = compile_lstm_crf(self.encoder, device)
+                self._plan = compile_lstm_crf(self.encoder, device, quantize=bool((self._native or {}).get("quantize")))
         return self._plan
 
     def invalidate_plan(self):

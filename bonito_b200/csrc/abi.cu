@@ -48,6 +48,10 @@ int launch_lstm_crf_fwd(const b200_lstm_crf_plan* p, const __half* x, __half* sc
 
 int copy_attention_timeline(long long* host_out, int max_tiles);
 
+int launch_quantize_i8(const __half* x, int8_t* out, long long n, float scale, cudaStream_t stream);
+int launch_gemm_i8(const int8_t* A, long long lda, const int8_t* B, const float* col_scale, __half* C, long long ldc, int M,
+                   int N, int K, const GemmEpilogue& ep, int max_ctas, cudaStream_t stream);
+
 static thread_local char g_err[1024] = "";
 
 void b200_set_error(const char* fmt, ...) {
@@ -232,6 +236,32 @@ int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank
     B200_REQUIRE(scores && workspace && moves && sequence && qstring, "crf_decode: null pointer argument");
     return launch_crf_decode((const __half*)scores, n, t, state_len, blank_score, qscale, qbias, workspace,
                              (uint8_t*)moves, (uint8_t*)sequence, (uint8_t*)qstring, (cudaStream_t)stream);
+}
+
+int b200_quantize_i8(const void* x, void* out, long long n, float scale, void* stream) {
+    B200_REQUIRE(x && out && n >= 0, "quantize_i8: bad arguments");
+    return launch_quantize_i8((const __half*)x, (int8_t*)out, n, scale, (cudaStream_t)stream);
+}
+
+int b200_gemm_i8_fwd(const void* a, long long lda, const void* b, const void* col_scale, const void* bias, void* c,
+                     long long ldc, int m, int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
+                     long long stride_inner, long long stride_outer, int group, long long stride_group, int cb_width,
+                     int cb_rows, int max_ctas, void* stream) {
+    B200_REQUIRE(a && b && c && col_scale, "gemm_i8: null pointer argument");
+    B200_REQUIRE(m >= 0 && n > 0 && k > 0 && rows_inner > 0 && group >= 0 && n % 8 == 0 && ldc % 8 == 0,
+                 "gemm_i8: bad sizes m=%d n=%d k=%d", m, n, k);
+    B200_REQUIRE(cb_width >= 0 && cb_rows >= 0 && cb_width % 32 == 0, "gemm_i8: column blocks must be multiples of 32 columns");
+    if (m == 0) return 0;
+    GemmEpilogue ep;
+    ep.bias = (const __half*)bias;
+    ep.act = act;
+    ep.lo = lo;
+    ep.hi = hi;
+    ep.map = RowMap{rows_inner, valid_inner, stride_inner, stride_outer, group, stride_group};
+    ep.cb_width = cb_width;
+    ep.cb_rows = cb_rows;
+    return launch_gemm_i8((const int8_t*)a, lda, (const int8_t*)b, (const float*)col_scale, (__half*)c, ldc, m, n, k, ep, max_ctas,
+                          (cudaStream_t)stream);
 }
 
 int b200_lstm_crf_fwd(const b200_lstm_crf_plan* plan, const void* x, void* scores, void* stream) {

@@ -5,7 +5,7 @@
 //              into a 4-stage shared-memory ring, completion on mbarriers
 //   warp 1     MMA issuer: one lane issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16),
 //              accumulating in TMEM; tcgen05.commit releases ring slots / publishes accumulators
-//   warps 2-9  epilogue, two warps per 32-lane TMEM quarter taking alternate 32-column blocks: tcgen05.ld (32 lanes x
+//   warps 2-13 epilogue, three warps per 32-lane TMEM quarter taking every third 32-column block: tcgen05.ld (32 lanes x
 //              32 columns) -> bias -> fp16 rounding -> activation (or the fused SwiGLU product) -> row-remapped
 //              16-byte stores.  TMEM holds two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps
 //              the mainloop of tile i+1 (K is only 304..512 here, so the epilogue is as long as the mainloop).
@@ -13,6 +13,7 @@
 // the LSTM input projections and the LinearCRFEncoder (+Clamp) -- reference call sites
 // bonito/nn.py:226,235-241 (Conv1d), :366-370 (LSTM W_ih), :283-298 + :59-67 (Linear, Clamp).
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -22,8 +23,12 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, STAGES = 4;
-constexpr int THREADS = 320;         // TMA warp, MMA warp, 2 x 4 epilogue warps
-constexpr int EPI_WARPS = 8;
+// Three epilogue warps per TMEM lane quarter: with two, the MMA warp spent most of its waiting on `tempty` (ncu source page:
+// the epilogue's dependent tcgen05.ld -> convert -> st.shared -> shfl / ld.shared -> st.global chain is latency bound, issue
+// slots 34 % busy), tensor pipe 48 % active.
+constexpr int EPI_SETS = 3;
+constexpr int EPI_WARPS = 4 * EPI_SETS;
+constexpr int THREADS = (2 + EPI_WARPS) * 32;   // TMA warp, MMA warp, epilogue warps
 
 template <int BN>
 struct TcSmem {
@@ -31,7 +36,7 @@ struct TcSmem {
     static constexpr uint32_t kB = BN * BK * 2;         // 16 / 32 KB
     static constexpr uint32_t kStage = kA + kB;
     static constexpr uint32_t kEpi = STAGES * kStage;             // 8 epilogue warps x (32 rows x 64 B) transpose buffers
-    static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;    // 8 x 512 B: the tile's bias slice, one copy per warp
+    static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;    // 512 B per warp: the tile's bias slice
     static constexpr uint32_t kBars = kBias + EPI_WARPS * 512;    // mbarriers after the buffers
     static constexpr uint32_t kTileQ = kBars + 160;               // dynamic tile queue: TQ mbarriers + TQ ints
     static constexpr uint32_t kTotal = kBars + 384 + 1024;   // + alignment slack
@@ -92,7 +97,7 @@ __device__ __forceinline__ void stage_bias(__half* sbias, const __half* __restri
     __syncwarp();
 }
 
-// Epilogue of one 128 x BN accumulator tile.  Two warps share each 32-lane TMEM quarter (= 32 output rows): warp set
+// Epilogue of one 128 x BN accumulator tile.  EPI_SETS warps share each 32-lane TMEM quarter (= 32 output rows): warp set
 // `set` takes every other 32-column block, so the two sets drain one accumulator in half the time (the kernels were
 // epilogue-bound with a single set: tile period 5.6k cycles against a 3.4k-cycle mainloop).  A lane owns one row; a block
 // of 32 columns is converted, transposed through a swizzled 32 x 64 B shared-memory buffer and written so that 4 lanes
@@ -100,13 +105,15 @@ __device__ __forceinline__ void stage_bias(__half* sbias, const __half* __restri
 template <int V>
 struct ActC { static constexpr int value = V; };
 
-template <int BN>
+template <int BN, int I8 = 0>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* tbuf, const __half* sbias,
                                               __half* __restrict__ C, long long ldc, int M, int N, int mb, int nb,
-                                              int quarter, int set, int lane, const GemmEpilogue& ep) {
+                                              int quarter, int set, int lane, const GemmEpilogue& ep,
+                                              const float* sscale = nullptr) {
     const int gm = mb * BM + quarter * 32 + lane;
     const long long orow = (gm < M) ? map_row(ep.map, gm) : -1;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+    const int cb_shift = (ep.cb_width > 0 && (ep.cb_width & (ep.cb_width - 1)) == 0) ? __ffs(ep.cb_width) - 1 : -1;
     // 64-B rows: the row's parity picks the half of a 128-B line, (row >> 1) & 3 permutes the four 16-B slots
     auto stage = [&](int g, const __half2 (&packed)[4]) {
         *reinterpret_cast<uint4*>(tbuf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(packed);
@@ -119,7 +126,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* 
         long long row_add = 0;
         int ocol = gcol;
         if (ep.cb_width > 0) {
-            const int cb = gcol / ep.cb_width;
+            const int cb = cb_shift >= 0 ? (gcol >> cb_shift) : gcol / ep.cb_width;
             row_add = (long long)cb * ep.cb_rows;
             ocol = gcol - cb * ep.cb_width;
         }
@@ -135,7 +142,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* 
     if (ep.act == B200_ACT_SWIGLU) {
         // columns [c0, c0+32) = y, [c0+32, c0+64) = gate of the same 32 features -> 32 outputs per row
 #pragma unroll 1
-        for (int c0 = set * 64; c0 < BN; c0 += 128) {
+        for (int c0 = set * 64; c0 < BN; c0 += 64 * EPI_SETS) {
             const int gn0 = nb * BN + c0;
             if (gn0 >= N) break;  // warp-uniform
             uint32_t vy[32], vg[32];
@@ -163,7 +170,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* 
     auto block = [&](auto act_c) {
         constexpr int ACT = decltype(act_c)::value;
 #pragma unroll 1
-        for (int c0 = set * 32; c0 < BN; c0 += 64) {
+        for (int c0 = set * 32; c0 < BN; c0 += 32 * EPI_SETS) {
             const int gn0 = nb * BN + c0;
             if (gn0 >= N) break;  // warp-uniform
             uint32_t v[32];
@@ -177,8 +184,14 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* 
                 const __half2* bh = reinterpret_cast<const __half2*>(&braw);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float x0 = __uint_as_float(v[g * 8 + 2 * p]) + __low2float(bh[p]);
-                    const float x1 = __uint_as_float(v[g * 8 + 2 * p + 1]) + __high2float(bh[p]);
+                    float x0, x1;
+                    if (I8) {   // s32 accumulators of the int8 product, de-quantised with the column's scale
+                        x0 = fmaf((float)(int)v[g * 8 + 2 * p], sscale[c0 + g * 8 + 2 * p], __low2float(bh[p]));
+                        x1 = fmaf((float)(int)v[g * 8 + 2 * p + 1], sscale[c0 + g * 8 + 2 * p + 1], __high2float(bh[p]));
+                    } else {
+                        x0 = __uint_as_float(v[g * 8 + 2 * p]) + __low2float(bh[p]);
+                        x1 = __uint_as_float(v[g * 8 + 2 * p + 1]) + __high2float(bh[p]);
+                    }
                     if (ACT == B200_ACT_NONE)
                         packed[p] = __floats2half2_rn(x0, x1);
                     else
@@ -197,6 +210,9 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* 
         default: block(ActC<B200_ACT_NONE>()); break;
     }
 }
+
+constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+static_assert(TcSmem<256>::kTotal <= SMEM_LIMIT, "streaming kernel: shared memory");
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -330,24 +346,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // A: 294 KB of L2 traffic per tile made the LSTM input projection L2-bandwidth bound (~5.4 TB/s of L2 reads).  Here a
 // CTA is bound to ONE column block of B, loads it once into shared memory (<= 144 KB) and streams only A tiles through
 // a 3-stage ring: 98 KB of L2 traffic per tile.
-constexpr int WS_STAGES = 3, WS_KB = 6;  // K <= 384
+constexpr int WS_KB = 6;
+constexpr int WSC_DEFAULT_BN = 0, WSC_DEFAULT_CL = 0;   // multicast-cluster variant: off unless B200_GEMM_CLUSTER selects a shape  // K <= 384 fp16 (K <= 768 int8: a 128-byte row holds 64 halves or 128 bytes)
 
-template <int BN>
+// INT8 variant (I8 = 1; the reference's --quantize path runs koi's int8 LSTM, bonito/crf/model.py:245): A and B are int8 with
+// 128-element (128-byte) K blocks, tcgen05.mma kind::i8 accumulates s32 in tensor memory, the epilogue multiplies by a
+// per-column scale.  The resident B block shrinks to half, which pays for a 6-stage A ring (3 for fp16): the fp16 kernel is
+// starved by the bytes it can keep in flight.
+template <int BN, int I8 = 0>
 struct WsSmem {
-    static constexpr uint32_t kBres = 0;                                  // [WS_KB][BN rows][128 B] SWIZZLE_128B
-    static constexpr uint32_t kRing = WS_KB * BN * 128;                   // WS_STAGES x (128 x 64 fp16)
-    static constexpr uint32_t kEpi = kRing + WS_STAGES * BM * BK * 2;     // 8 x 2 KB transpose buffers
-    static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;            // 8 x 512 B bias slice copies
-    static constexpr uint32_t kBars = kBias + EPI_WARPS * 512;
+    static constexpr int kStages = I8 ? 6 : 3;
+    static constexpr int kKb = I8 ? WS_KB / 2 : WS_KB;
+    static constexpr uint32_t kBres = 0;                                  // [kKb][BN rows][128 B] SWIZZLE_128B
+    static constexpr uint32_t kRing = kKb * BN * 128;                     // kStages x (128 rows x 128 B)
+    static constexpr uint32_t kEpi = kRing + kStages * BM * BK * 2;       // 2 KB transpose buffer per warp
+    static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;            // 512 B bias slice copy per warp
+    static constexpr uint32_t kScale = kBias + EPI_WARPS * 512;           // I8: 8 x 1 KB column-scale copies (float)
+    static constexpr uint32_t kBars = kScale + (I8 ? EPI_WARPS * 1024 : 0);
     static constexpr uint32_t kTileQ = kBars + 160;                       // dynamic tile queue: TQ mbarriers + TQ ints
     static constexpr uint32_t kTotal = kBars + 384 + 1024;
 };
 
-template <int BN>
+static_assert(WsSmem<192, 0>::kTotal <= SMEM_LIMIT && WsSmem<192, 1>::kTotal <= SMEM_LIMIT, "weight-stationary kernel: shared memory");
+
+template <int BN, int I8 = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep, int* __restrict__ ctr) {
-    using S = WsSmem<BN>;
+               __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep, int* __restrict__ ctr,
+               const float* __restrict__ col_scale) {
+    using S = WsSmem<BN, I8>;
+    constexpr int WS_STAGES = S::kStages;
+    constexpr int KE = I8 ? 2 * BK : BK;          // K elements per 128-byte block
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + S::kBars;
@@ -364,7 +393,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
-    const int k_blocks = (K + BK - 1) / BK;
+    const int k_blocks = (K + KE - 1) / KE;
     const int nb = blockIdx.x % n_blocks;                 // this CTA's column block, for its whole life; row blocks by ticket
 
     if (warp == 0 && lane == 0) {
@@ -395,7 +424,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (mb < m_blocks) {      // a CTA that starts after the column block is exhausted does not even load B
                 mbar_expect_tx(bres_bar, (uint32_t)k_blocks * BN * 128);
                 for (int kb = 0; kb < k_blocks; ++kb)
-                    tma_load_2d(base + S::kBres + kb * (BN * 128), &map_b, bres_bar, kb * BK, nb * BN);
+                    tma_load_2d(base + S::kBres + kb * (BN * 128), &map_b, bres_bar, kb * KE, nb * BN);
             }
             int stage = 0;
             uint32_t phase = 0;
@@ -406,7 +435,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), BM * BK * 2);
-                    tma_load_2d(base + S::kRing + stage * (BM * BK * 2), &map_a, full_bar(stage), kb * BK, mb * BM);
+                    tma_load_2d(base + S::kRing + stage * (BM * BK * 2), &map_a, full_bar(stage), kb * KE, mb * BM);
                     if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
                 }
                 mb = next;
@@ -415,7 +444,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (elect_one_sync()) {
-            const uint32_t idesc = tc_idesc_f16(BM, BN);
+            // kind::i8 descriptor: D = s32 (2 at [4,6)), A = B = signed 8-bit (1 at [7,10) and [10,13)), K-major
+            const uint32_t idesc = I8 ? ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24))
+                                      : tc_idesc_f16(BM, BN);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int q = 0; tq.take(q) >= 0; ++q) {
@@ -429,8 +460,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint64_t adesc = tc_smem_desc_sw128(base + S::kRing + stage * (BM * BK * 2));
                     const uint64_t bdesc = tc_smem_desc_sw128(base + S::kBres + kb * (BN * 128));
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        tc_mma_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {    // 32 bytes of K per instruction: 16 halves or 32 int8
+                        if (I8) tc_mma_ss_i8(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else tc_mma_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     tc_commit(empty_bar(stage));
                     if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -444,6 +477,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         unsigned char* tbuf = gen_base + S::kEpi + ew * 2048;
         __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + ew * 512);
         stage_bias<BN>(sbias, ep.bias, nb, N, lane);       // the column block never changes
+        float* sscale = nullptr;
+        if (I8) {
+            sscale = reinterpret_cast<float*>(gen_base + S::kScale + ew * 1024);
+            for (int i = lane; i < BN; i += 32) sscale[i] = (nb * BN + i < N) ? col_scale[nb * BN + i] : 0.f;
+            __syncwarp();
+        }
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int q = 0;; ++q) {
@@ -451,7 +490,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (mb < 0) break;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, set, lane, ep);
+            epilogue_tile<BN, I8>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, set, lane, ep, sscale);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -463,6 +502,189 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     if (warp == 1) tc_dealloc(tmem_base, BN <= 128 ? 256 : 512);
     if (threadIdx.x == 0) release_tile_counters(ctr, n_blocks);
+}
+
+
+// ---- weight-stationary, A multicast across a cluster ------------------------------------------------------------------
+// The weight-stationary kernel above streams every 128 x K tile of A once PER COLUMN BLOCK (8 times for the LSTM input
+// projection at BN = 192) and can keep only 3 x 16 KB of A in flight next to its 144 KB of resident weights: per SM it needs
+// 42 B/clk of A at full tensor rate, and 48 KB in flight at ~1.5k cycles of loaded L2 latency deliver ~27 (measured: 0.62
+// of the cuBLAS rate).  Here CL CTAs of a cluster own CL ADJACENT column blocks and work on the SAME row block: each CTA
+// fetches 128/CL rows of every A stage and TMA-multicasts them into the ring of all CL CTAs (L2 reads of A divided by CL),
+// a ring slot is re-filled once the MMAs of all CL CTAs have drained it (tcgen05.commit multicast onto every CTA's
+// `empty` barrier, count CL), and BN = 128 halves the resident block, which pays for a 6-stage ring.  Row blocks are handed
+// out per cluster: rank 0 draws the ticket and posts it into every CTA's tile queue through distributed shared memory.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n" ::
+            "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v) {
+    asm volatile("st.shared::cluster.s32 [%0], %1;\n" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+
+template <int BN>
+struct WcSmem {
+    static constexpr int kStages = BN <= 128 ? 6 : 3;
+    static constexpr uint32_t kBres = 0;                                  // [WS_KB][BN rows][128 B] SWIZZLE_128B
+    static constexpr uint32_t kRing = WS_KB * BN * 128;                   // kStages x (128 rows x 128 B)
+    static constexpr uint32_t kEpi = kRing + kStages * BM * BK * 2;
+    static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;
+    static constexpr uint32_t kBars = kBias + EPI_WARPS * 512;            // 2 * kStages + 6 mbarriers
+    static constexpr uint32_t kTileQ = kBars + 8 * (2 * kStages + 6);     // TQ mbarriers + TQ ints
+    static constexpr uint32_t kTotal = kTileQ + 12 * TQ + 64 + 1024;
+};
+
+static_assert(WcSmem<192>::kTotal <= SMEM_LIMIT && WcSmem<128>::kTotal <= SMEM_LIMIT, "multicast kernel: shared memory");
+
+template <int BN, int CL>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_wsc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep, int* __restrict__ ctr) {
+    using S = WcSmem<BN>;
+    constexpr int ST = S::kStages;
+    constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
+    constexpr int SLICE_ROWS = BM / CL;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + S::kBars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (ST + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * ST + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * ST + 2 + s); };
+    const uint32_t bres_bar = bars + 8u * (2 * ST + 4);
+    const uint32_t tmem_slot = bars + 8u * (2 * ST + 5);
+    unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t tq_bars = base + S::kTileQ, tq_tiles = base + S::kTileQ + 8 * TQ;
+    volatile int* tq_tiles_gen = reinterpret_cast<volatile int*>(gen_base + S::kTileQ + 8 * TQ);
+    auto take = [&](int q) {   // the ticket was posted by rank 0 of the cluster (possibly this CTA) through shared::cluster
+        mbar_wait_cluster(tq_bars + 8u * (uint32_t)(q & (TQ - 1)), (uint32_t)((q / TQ) & 1));
+        return tq_tiles_gen[q & (TQ - 1)];
+    };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, groups = n_blocks / CL;
+    const int k_blocks = (K + BK - 1) / BK;
+    const int grp = (int)(blockIdx.x / CL) % groups;      // column group of this cluster, for its whole life
+    const int nb = grp * CL + (int)rank;                  // this CTA's column block
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a));
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b));
+        for (int s = 0; s < ST; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), CL);       // one tcgen05.commit per CTA of the cluster
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), EPI_WARPS);
+        }
+        mbar_init(bres_bar, 1);
+        for (int s = 0; s < TQ; ++s) mbar_init(tq_bars + 8u * s, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tc_alloc(tmem_slot, BN <= 128 ? 256 : 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // every CTA's barriers exist before a peer's multicast or ticket can land
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + S::kBars + 8u * (2 * ST + 5));
+
+    if (warp == 0) {
+        // ===== TMA producer: B once, then this CTA's slice of every A stage, multicast to the cluster =====
+        if (elect_one_sync()) {
+            auto post = [&](int q, int tile) {     // rank 0: ticket -> every CTA's queue slot, then its barrier (release.cluster)
+                const uint32_t slot = (uint32_t)(q & (TQ - 1));
+                for (uint32_t r = 0; r < (uint32_t)CL; ++r) {
+                    st_cluster_s32(mapa(tq_tiles + 4u * slot, r), tile);
+                    mbar_arrive_remote(mapa(tq_bars + 8u * slot, r));
+                }
+            };
+            int stage = 0;
+            uint32_t phase = 0;
+            int next = 0;
+            if (rank == 0) {
+                const int first = atomicAdd(&ctr[grp], 1);
+                post(0, first < m_blocks ? first : -1);
+            }
+            for (int q = 0;; ++q) {
+                const int mb = take(q);
+                if (mb < 0) break;
+                if (rank == 0) next = atomicAdd(&ctr[grp], 1);   // its latency hides behind the loads below
+                if (q == 0) {
+                    mbar_expect_tx(bres_bar, (uint32_t)k_blocks * BN * 128);
+                    for (int kb = 0; kb < k_blocks; ++kb)
+                        tma_load_2d(base + S::kBres + kb * (BN * 128), &map_b, bres_bar, kb * BK, nb * BN);
+                }
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);      // drained by the MMAs of all CL CTAs
+                    mbar_expect_tx(full_bar(stage), BM * BK * 2);
+                    tma_load_2d_mc(base + S::kRing + stage * (BM * BK * 2) + rank * (SLICE_ROWS * 128), &map_a, full_bar(stage),
+                                   kb * BK, mb * BM + (int)rank * SLICE_ROWS, MASK);
+                    if (++stage == ST) { stage = 0; phase ^= 1; }
+                }
+                if (rank == 0) post(q + 1, next < m_blocks ? next : -1);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one_sync()) {
+            const uint32_t idesc = tc_idesc_f16(BM, BN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int q = 0; take(q) >= 0; ++q) {
+                if (q == 0) mbar_wait(bres_bar, 0);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = tc_smem_desc_sw128(base + S::kRing + stage * (BM * BK * 2));
+                    const uint64_t bdesc = tc_smem_desc_sw128(base + S::kBres + kb * (BN * 128));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc_mma_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_mc(empty_bar(stage), MASK);        // this CTA is done with the slot: tell every producer
+                    if (++stage == ST) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int quarter = warp & 3, ew = warp - 2, set = ew >> 2;
+        unsigned char* tbuf = gen_base + S::kEpi + ew * 2048;
+        __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + ew * 512);
+        stage_bias<BN>(sbias, ep.bias, nb, N, lane);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int q = 0;; ++q) {
+            const int mb = take(q);
+            if (mb < 0) break;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            epilogue_tile<BN, 0>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, set, lane, ep);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc_dealloc(tmem_base, BN <= 128 ? 256 : 512);
+    cluster_sync_all();      // nobody leaves while a peer's commit may still arrive on this CTA's barriers
+    if (threadIdx.x == 0) release_tile_counters(ctr, groups);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -482,15 +704,15 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D fp16 tensor [rows][cols] with row stride `ld` elements, box = box_rows x 64, 128-B swizzle.
-int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+// 2-D fp16 (or int8) tensor [rows][cols] with row stride `ld` elements, box = box_rows x 128 bytes, 128-B swizzle.
+int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows, bool i8 = false) {
     EncodeTiledFn fn = get_encode_fn();
     B200_REQUIRE(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (i8 ? 1 : 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(i8 ? 2 * BK : BK), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = fn(map, i8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
@@ -560,16 +782,16 @@ int launch_tc(const __half* A, long long lda, const __half* B, __half* C, long l
     return 0;
 }
 
-template <int BN>
-int launch_ws(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
-              const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
+template <int BN, int I8 = 0>
+int launch_ws(const void* A, long long lda, const void* B, __half* C, long long ldc, int M, int N, int K,
+              const GemmEpilogue& ep, int max_ctas, cudaStream_t stream, const float* col_scale = nullptr) {
     CUtensorMap map_a, map_b;
-    int rc = make_map(&map_a, A, M, K, lda, BM);
+    int rc = make_map(&map_a, A, M, K, lda, BM, I8);
     if (rc) return rc;
-    rc = make_map(&map_b, B, N, K, K, BN);
+    rc = make_map(&map_b, B, N, K, K, BN, I8);
     if (rc) return rc;
-    auto kern = gemm_ws_kernel<BN>;
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem<BN>::kTotal));
+    auto kern = gemm_ws_kernel<BN, I8>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem<BN, I8>::kTotal));
     int dev = 0, sms = 0;
     B200_CHECK_CUDA(cudaGetDevice(&dev));
     B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -581,8 +803,68 @@ int launch_ws(const __half* A, long long lda, const __half* B, __half* C, long l
     int* ctr = nullptr;
     rc = take_counters(n_blocks + 1, stream, &ctr);
     if (rc) return rc;
-    kern<<<per_block * n_blocks, THREADS, WsSmem<BN>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep, ctr);
+    kern<<<per_block * n_blocks, THREADS, WsSmem<BN, I8>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep, ctr, col_scale);
     B200_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// cluster shape of the multicast kernel: B200_GEMM_CLUSTER = "<BN>x<CL>" (128x2, 128x4, 192x2, 192x4) or "0" (off)
+static void cluster_shape(int* bn, int* cl) {
+    static int s_bn = -1, s_cl = 0;
+    if (s_bn < 0) {
+        int b = WSC_DEFAULT_BN, c = WSC_DEFAULT_CL;
+        const char* e = getenv("B200_GEMM_CLUSTER");
+        if (e && e[0] == '0') b = c = 0;
+        else if (e && sscanf(e, "%dx%d", &b, &c) != 2) { b = WSC_DEFAULT_BN; c = WSC_DEFAULT_CL; }
+        s_cl = c;
+        s_bn = b;
+    }
+    *bn = s_bn;
+    *cl = s_cl;
+}
+
+template <int BN, int CL>
+int launch_wsc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
+               const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, A, M, K, lda, BM / CL);
+    if (rc) return rc;
+    rc = make_map(&map_b, B, N, K, K, BN);
+    if (rc) return rc;
+    auto kern = gemm_wsc_kernel<BN, CL>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WcSmem<BN>::kTotal));
+    int dev = 0, sms = 0;
+    B200_CHECK_CUDA(cudaGetDevice(&dev));
+    B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+    const int m_blocks = (M + BM - 1) / BM, groups = N / BN / CL;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = WcSmem<BN>::kTotal;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int s_max_clusters = 0;             // per (BN, CL) instantiation: co-resident clusters on an idle device
+    if (s_max_clusters == 0) {
+        cfg.gridDim = dim3(CL * 64);
+        int n = 0;
+        B200_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        s_max_clusters = n > 0 ? n : 1;
+    }
+    int clusters = sms / CL < s_max_clusters ? sms / CL : s_max_clusters;
+    int per_group = clusters / groups;
+    if (per_group > m_blocks) per_group = m_blocks;
+    if (per_group < 1) per_group = 1;
+    cfg.gridDim = dim3(per_group * groups * CL);
+    int* ctr = nullptr;
+    rc = take_counters(groups + 1, stream, &ctr);
+    if (rc) return rc;
+    B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, C, ldc, M, N, K, ep, ctr));
     return 0;
 }
 
@@ -594,8 +876,29 @@ int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, l
                  "gemm_tc: operands must be 16-byte aligned");
     const char* env = getenv("B200_GEMM_WS");
     const bool ws_ok = !(env && env[0] == '0') && K <= WS_KB * BK && M >= 4 * BM;
-    if (ws_ok && N % 192 == 0 && N / 192 <= 64) return launch_ws<192>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
-    if (ws_ok && N % 128 == 0 && N / 128 <= 64) return launch_ws<128>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+    int cbn = 0, ccl = 0;
+    cluster_shape(&cbn, &ccl);
+    if (ws_ok && ccl > 1 && M >= 64 * BM && N % (cbn * ccl) == 0 && N / cbn <= 64) {
+        if (cbn == 128 && ccl == 2) return launch_wsc<128, 2>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+        if (cbn == 128 && ccl == 4) return launch_wsc<128, 4>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+        if (cbn == 192 && ccl == 2) return launch_wsc<192, 2>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+        if (cbn == 192 && ccl == 4) return launch_wsc<192, 4>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+    }
+    if (ws_ok && N % 192 == 0 && N / 192 <= 64) return launch_ws<192, 0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+    if (ws_ok && N % 128 == 0 && N / 128 <= 64) return launch_ws<128, 0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     if (N % 256 == 0) return launch_tc<256>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     return launch_tc<128>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+}
+
+// C = act(scale[col] * (A_i8 B_i8^T) + bias): int8 operands (A [M][K] row stride lda bytes, B [N][K]), s32 accumulation on
+// kind::i8 tensor cores, weight-stationary kernel only (K <= 768, N a multiple of 192 or 128).
+int launch_gemm_i8(const int8_t* A, long long lda, const int8_t* B, const float* col_scale, __half* C, long long ldc, int M,
+                   int N, int K, const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
+    B200_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0 && col_scale != nullptr,
+                 "gemm_i8: operands must be 16-byte aligned and a column scale is required");
+    B200_REQUIRE(K % 16 == 0 && lda % 16 == 0 && K <= WS_KB * BK && ep.act != B200_ACT_SWIGLU,
+                 "gemm_i8: K (%d) and lda (%lld) must be multiples of 16 bytes, K <= %d", K, lda, WS_KB * BK);
+    if (N % 192 == 0 && N / 192 <= 64) return launch_ws<192, 1>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream, col_scale);
+    B200_REQUIRE(N % 128 == 0 && N / 128 <= 64, "gemm_i8: N (%d) must be a multiple of 192 or 128", N);
+    return launch_ws<128, 1>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream, col_scale);
 }

@@ -103,7 +103,7 @@ class _StreamStage(_Stage):
 class LstmCrfPlan:
     """Packed weights + cached buffers for one LSTM-CRF encoder on one device."""
 
-    def __init__(self, encoder, device):
+    def __init__(self, encoder, device, quantize=False):
         layers = list(encoder.children())
         convs = [m for m in layers if isinstance(m, bnn.Convolution)]
         lstms = [m for m in layers if isinstance(m, bnn.LSTM)]
@@ -163,6 +163,17 @@ class LstmCrfPlan:
                 whh=_dev16(r.weight_hh_l0.detach().cpu()[perm_hh], device),
                 reverse=bool(m.reverse),
             ))
+            if quantize:
+                # --quantize (reference: koi's int8 LSTM, bonito/crf/model.py:245): the input projection runs on int8 tensor
+                # cores.  Weights: symmetric per-row int8; activations: LSTM inputs live in (-1, 1) (tanh / o*tanh(c)), fixed
+                # scale 127.  gx = (q_x . q_w) * s_w / 127 + bias.  The recurrent weights and the h exchange stay fp16.
+                w = r.weight_ih_l0.detach().float().cpu()[perm_ih]
+                s_w = w.abs().amax(dim=1).clamp(min=1e-8) / 127.0
+                self.lstm[-1]["wih_q"] = torch.round(w / s_w[:, None]).clamp(-127, 127).to(torch.int8).to(device).contiguous()
+                self.lstm[-1]["wih_scale"] = (s_w / 127.0).to(device=device, dtype=torch.float32).contiguous()
+        self.quantize = bool(quantize)
+        if self.quantize and not (self.tile and H % 16 == 0):
+            raise UnsupportedModel("the int8 input projection (--quantize) needs the tile-layout LSTM path (hidden size 384)")
 
         # --- linear CRF head (+ clamp) ---------------------------------------------------------
         crf = crfs[0]
@@ -366,6 +377,7 @@ class LstmCrfPlan:
                 ya=torch.zeros(nt, T, TB, H, dtype=f16, device=dev),
                 yb=torch.zeros(nt, T, TB, H, dtype=f16, device=dev),
                 gx=torch.zeros(nt, T, self.tile_cs, TB, 4 * H // self.tile_cs, dtype=f16, device=dev),
+                yq=torch.empty(nt * T * TB * H, dtype=torch.int8, device=dev) if self.quantize else None,
                 # staging of the recurrent kernel's h all-gather: one region per tile (tiles run concurrently)
                 hx=torch.empty(nt, native.lstm_rec_tile_workspace_bytes(TB), dtype=torch.uint8, device=dev),
                 streams=[torch.cuda.Stream(device=dev) for _ in range(nt)],
@@ -433,6 +445,16 @@ class LstmCrfPlan:
 
         def in_gemm(src, layer, tiles, st, max_ctas=0):      # rows (tile, t, chunk) -> gx[tile][t][rank][chunk][CW]
             i0, cnt = tiles
+            if self.quantize:
+                rows = cnt * T * TB
+                yq = b["yq"][i0 * T * TB * H:]
+                with staged("quantize_i8", st):
+                    native.quantize_i8(src[i0:i0 + cnt], yq[:rows * H], 127.0, stream=st)
+                with staged("lstm_in_gemm", st):
+                    native.gemm_i8(yq, H, layer["wih_q"], layer["wih_scale"], layer["bias"], b["gx"][i0], CW, rows, 4 * H, H,
+                                   rows_inner=TB, valid_inner=TB, stride_inner=1, stride_outer=CS * TB, cb_width=CW,
+                                   cb_rows=TB, stream=st, max_ctas=max_ctas)
+                return
             with staged("lstm_in_gemm", st):
                 native.gemm(src[i0], H, layer["wih"], layer["bias"], b["gx"][i0], CW, cnt * T * TB, 4 * H, H,
                             rows_inner=TB, valid_inner=TB, stride_inner=1, stride_outer=CS * TB, cb_width=CW, cb_rows=TB,
@@ -456,7 +478,7 @@ class LstmCrfPlan:
         def gather(buf):            # [tile][T][48][H] -> [T][N][H]
             return buf.permute(1, 0, 2, 3).reshape(T, nt * TB, H)[:, :N].clone()
 
-        if not streams and events is None and not return_features and gemm_impl == native.GEMM_AUTO \
+        if not streams and events is None and not return_features and gemm_impl == native.GEMM_AUTO and not self.quantize \
                 and len(self.lstm) <= native.MAX_LSTM_LAYERS and os.environ.get("B200_COARSE_FWD", "1") != "0":
             # the whole encoder from ONE C-ABI call (b200_lstm_crf_fwd); the per-kernel path below runs the same launches
             # one ctypes call at a time (used when per-kernel events or intermediate activations are wanted)
@@ -623,8 +645,8 @@ class _DecodeCache:
 DECODE_CACHE = _DecodeCache()
 
 
-def compile_lstm_crf(encoder, device):
-    return LstmCrfPlan(encoder, device)
+def compile_lstm_crf(encoder, device, quantize=False):
+    return LstmCrfPlan(encoder, device, quantize=quantize)
 
 
 class CrfDecoder:

@@ -67,6 +67,10 @@ SIGNATURES = {
     "b200_debug_exchange_bench": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "b200_quantize_i8": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_void_p]),
+    "b200_gemm_i8_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                                 c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_longlong, c_int, c_int,
+                                 c_int, c_void_p]),
     "b200_lstm_crf_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_crf_beam_search": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -312,3 +316,26 @@ def lstm_crf_fwd(plan_struct, x, scores, stream=None):
         rc = lib.b200_lstm_crf_fwd(ctypes.byref(plan_struct), _ptr(_f16(x, "x")), _ptr(scores), _stream(stream))
     _check(rc, "b200_lstm_crf_fwd")
     return scores
+
+
+def quantize_i8(x, out, scale=127.0, stream=None):
+    """fp16 -> int8 (see b200_quantize_i8); `out`: int8 tensor with x.numel() elements."""
+    lib = require()
+    with torch.cuda.device(out.device):
+        rc = lib.b200_quantize_i8(_ptr(_f16(x, "x")), _ptr(out), x.numel(), float(scale), _stream(stream))
+    _check(rc, "b200_quantize_i8")
+    return out
+
+
+def gemm_i8(a, lda, b, col_scale, bias, c, ldc, m, n, k, act=ACT_NONE, lo=0.0, hi=0.0, rows_inner=None, valid_inner=None,
+            stride_inner=1, stride_outer=0, group=0, stride_group=0, cb_width=0, cb_rows=0, stream=None, max_ctas=0):
+    """C = act(col_scale * (A_i8 B_i8^T) + bias) (see b200_gemm_i8_fwd)."""
+    lib = require()
+    if rows_inner is None:
+        rows_inner, valid_inner = m, m
+    with torch.cuda.device(c.device):
+        rc = lib.b200_gemm_i8_fwd(_ptr(a), lda, _ptr(b), _ptr(col_scale), _ptr(bias), _ptr(c), ldc, m, n, k, act, float(lo),
+                                  float(hi), rows_inner, valid_inner, stride_inner, stride_outer, int(group), int(stride_group),
+                                  int(cb_width), int(cb_rows), int(max_ctas), _stream(stream))
+    _check(rc, "b200_gemm_i8_fwd")
+    return c

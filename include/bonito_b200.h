@@ -210,6 +210,19 @@ int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank
                     void* workspace, void* moves, void* sequence, void* qstring, void* stream);
 
 /*
+ * ---- INT8 input projection (--quantize; reference: koi's int8 LSTM path, bonito/crf/model.py:245, cli/basecaller.py:186-189) ----
+ * b200_quantize_i8: out[i] = clamp(rint(x[i] * scale), -127, 127), fp16 -> int8, n a multiple of 8.
+ * b200_gemm_i8_fwd: C = act(col_scale[j] * sum_k A_i8[i][k] B_i8[j][k] + bias[j]) -- int8 operands (lda in bytes), s32
+ *   accumulation on tcgen05 kind::i8, per-column float scale (weight scale / activation scale), fp16 bias / output, the
+ *   same row / column-block maps as b200_gemm_fwd_ex.  K <= 768, K % 16 == 0, N a multiple of 192 or 128.
+ */
+int b200_quantize_i8(const void* x, void* out, long long n, float scale, void* stream);
+int b200_gemm_i8_fwd(const void* a, long long lda, const void* b, const void* col_scale, const void* bias, void* c,
+                     long long ldc, int m, int n, int k, int act, float lo, float hi, int rows_inner, int valid_inner,
+                     long long stride_inner, long long stride_outer, int group, long long stride_group, int cb_width,
+                     int cb_rows, int max_ctas, void* stream);
+
+/*
  * ---- coarse entry point: the whole LSTM-CRF encoder forward of one batch from one call ----
  * conv stem -> strided convolution (GEMM) -> n_lstm x (input projection GEMM + persistent recurrent layer) ->
  * LinearCRFEncoder GEMM (+Clamp), enqueued on `stream` (14 launches for the hac shape).  Replaces the module-tree walk of

@@ -189,6 +189,42 @@ def test_lstm_tile_kernel_matches_oracle(native, n, t, reverse):
     assert torch.equal(y_old.cpu(), y.cpu().permute(1, 0, 2, 3).reshape(t, nt * tb, H)[:, :n])
 
 
+@pytest.mark.parametrize("m,n,k,bias,cb", [(1000, 1536, 384, True, False), (4096 + 77, 384, 256, False, False),
+                                           (37 * 48, 1536, 384, True, True)])
+def test_gemm_int8_matches_integer_matmul(native, m, n, k, bias, cb):
+    """tcgen05 kind::i8: exact s32 accumulation of int8 products, per-column scale and bias in the epilogue."""
+    g = torch.Generator().manual_seed(m + n)
+    a = torch.randint(-127, 128, (m, k), generator=g, dtype=torch.int8)
+    w = torch.randint(-127, 128, (n, k), generator=g, dtype=torch.int8)
+    scale = (torch.rand(n, generator=g) * 2e-4 + 1e-5).float()
+    bv = torch.randn(n, generator=g).half() if bias else None
+    acc = (a.double() @ w.double().T)                      # exact integers
+    ref = (acc * scale.double() + (bv.double() if bias else 0.0)).float().half().float()
+    if cb:
+        t, tb, cs, cw = 37, 48, 6, 256
+        out = torch.full((t, cs, tb, cw), float("nan"), dtype=torch.float16, device="cuda")
+        native.gemm_i8(a.cuda(), k, w.cuda(), scale.cuda(), None if bv is None else bv.cuda(), out, cw, m, n, k, rows_inner=tb,
+                       valid_inner=tb, stride_inner=1, stride_outer=cs * tb, cb_width=cw, cb_rows=tb)
+        got = out.float().cpu().permute(0, 2, 1, 3).reshape(m, n)
+    else:
+        out = torch.full((m, n), float("nan"), dtype=torch.float16, device="cuda")
+        native.gemm_i8(a.cuda(), k, w.cuda(), scale.cuda(), None if bv is None else bv.cuda(), out, n, m, n, k)
+        got = out.float().cpu()
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any()
+    err = (got - ref).abs()
+    assert bool(torch.all(err <= 2e-3 + 1e-3 * ref.abs())), err.max().item()     # one fp16 rounding of the result
+
+
+def test_quantize_i8(native):
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(4096 * 8, generator=g) * 0.6).clamp(-1.5, 1.5).half()
+    out = torch.empty(x.numel(), dtype=torch.int8, device="cuda")
+    native.quantize_i8(x.cuda(), out, 127.0)
+    want = torch.round(x.float() * 127.0).clamp(-127, 127).to(torch.int8)
+    assert torch.equal(out.cpu(), want)
+
+
 def test_tmem_conventions(native):
     """tcgen05.ld.16x256b fragment layout and the fp16-pair packing of a TMEM-resident A operand."""
     out = native.tmem_probe().numpy()

@@ -335,3 +335,30 @@ def test_reverse_complement_on_the_native_layout():
         # in-edge, lowest state) is not symmetric under reverse complement
         assert same >= 0.97, same
     print("reverse-complement basecalls identical to the reverse complement of the forward basecall:", exact, "of 5")
+
+
+def test_quantized_input_projection_stays_close_to_fp16():
+    """--quantize: int8 input projections (per-row weight scale, activations x127).  Its own parity budget: the scores of the
+    quantised model against the fp16 model of the same weights, and the base sequences of both by edit distance."""
+    from _helpers import identity
+    from bonito_b200.crf.model import Model
+    from bonito_b200.decode import beam_search, to_str
+    spec = synth.model_spec("hac")
+    weights = synth.make_weights(spec, seed=25)
+    x = synth.squiggle(50, 3996, seed=11).half().cuda()
+    out = {}
+    for q in (False, True):
+        model = Model(synth.model_config(spec))
+        model.load_state_dict(synth.state_dict_from_weights(spec, weights))
+        model.use_koi(batchsize=50, chunksize=3996, quantize=q)
+        model = model.half().eval().cuda()
+        with torch.inference_mode():
+            scores = model(x)
+            seq, _, _ = beam_search(scores)
+        out[q] = (scores.float().cpu(), [to_str(r) for r in seq])
+    err = (out[True][0] - out[False][0]).abs()
+    ids = [identity(a, b) for a, b in zip(out[True][1], out[False][1])]
+    print(f"int8 input projection vs fp16: scores max {err.max().item():.3f} mean {err.mean().item():.4f}; "
+          f"sequence identity mean {sum(ids) / len(ids):.4f} min {min(ids):.4f}")
+    assert err.mean().item() <= 0.08 and err.max().item() <= 3.0, (err.mean().item(), err.max().item())
+    assert sum(ids) / len(ids) >= 0.95 and min(ids) >= 0.85
