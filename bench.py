@@ -121,7 +121,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # models
 # ---------------------------------------------------------------------------------------------------------------
-def build_hac(device, rank, world, name="hac", batch=BATCH, chunk=CHUNK):
+def build_hac(device, rank, world, name="hac", batch=BATCH, chunk=CHUNK, quantize=False):
     from bonito_b200.crf.model import Model
     from bonito_b200 import synth
     spec = synth.model_spec(name)
@@ -131,7 +131,7 @@ def build_hac(device, rank, world, name="hac", batch=BATCH, chunk=CHUNK):
     if rank == 0:
         model.load_state_dict(synth.state_dict_from_weights(spec, weights))
     chunksize = chunk - chunk % model.stride
-    model.use_koi(batchsize=batch, chunksize=chunksize, quantize=False)
+    model.use_koi(batchsize=batch, chunksize=chunksize, quantize=quantize)
     model = model.half().eval().to(device)
     if world > 1:  # the one collective of the path: weights from rank 0 (NCCL over NVLink)
         from bonito_b200.distributed import broadcast_parameters
@@ -345,6 +345,32 @@ def bench_hac(ctx, peaks, sampler):
     }
     del model, plan
     return line, (spec, weights, L)
+
+
+def bench_hac_quantized(ctx):
+    """The `--quantize` option of the basecaller (int8 LSTM input projections): the headline shape once more, resident only.
+    A separate configuration: its scores differ from the fp16 path (tests/test_gpu_pipeline.py states the budget)."""
+    from bonito_b200 import synth
+    from bonito_b200.decode import _decoder
+    args, device = ctx.args, ctx.device
+    model, spec, _, L = build_hac(device, ctx.rank, ctx.world, batch=args.batch, quantize=True)
+    N = args.batch
+    x_dev = synth.squiggle(64, L, seed=100 + ctx.rank).repeat(N // 64 + 1, 1, 1)[:N].contiguous().to(device, torch.float16)
+    plan = model.native_plan(device)
+    qs = model.config["qscore"]
+
+    def step(events, slot):
+        scores = plan.forward(x_dev, events=None, slot=slot)
+        return _decoder(scores, spec["state_len"], blank_score=plan.blank_score, qscale=qs["scale"], qbias=qs["bias"], slot=slot)
+
+    steps = min(args.steps, 10)
+    elapsed_ms, _, _ = time_resident(ctx, step, steps, 3, None, slots=N_SLOTS if plan.supports_slots else 1)
+    (elapsed_ms,) = ctx.max_over_ranks([elapsed_ms])
+    del model, plan
+    torch.cuda.empty_cache()
+    return {"workload": f"hac-shaped LSTM-CRF, batch {N} x {L} samples, int8 input projections (basecaller --quantize)",
+            "value": ctx.world * N * L * steps / (elapsed_ms * 1e-3), "unit": "samples/s", "n_gpus": ctx.world, "steps": steps,
+            "warmup": 3, "ms_per_step": elapsed_ms / steps, "dtype": "i8 input projections, f16 elsewhere"}
 
 
 def sup_flops(spec, plan, N, L):
@@ -578,6 +604,11 @@ def main():
         torch.cuda.empty_cache()
 
         configs = {}
+        if args.workload in ("all", "hac"):
+            cq = bench_hac_quantized(ctx)
+            if rank == 0:
+                configs["hac_quantize_int8"] = cq
+                log(f"hac --quantize: {cq['ms_per_step']:.2f} ms/step")
         if args.workload in ("all", "sup"):
             model, spec = build_sup(device, rank, world)
             log("sup model built")

@@ -197,6 +197,11 @@ int b200_debug_attention_timeline(long long* host_out, int max_tiles) {
     return copy_attention_timeline(host_out, max_tiles);
 }
 
+int b200_debug_gemm_profile(long long* host_out) {
+    B200_REQUIRE(host_out != nullptr, "gemm_profile: null pointer argument");
+    return copy_gemm_profile(host_out);
+}
+
 int b200_debug_tmem_probe(void* out, void* stream) {
     B200_REQUIRE(out != nullptr, "tmem_probe: null pointer argument");
     return launch_tmem_probe((float*)out, (cudaStream_t)stream);

@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -341,13 +342,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (threadIdx.x == 0) release_tile_counters(ctr, 1);
 }
 
+// ---- where the cycles of the weight-stationary kernel go (B200_GEMM_DEBUG=1, scripts/gemm_profile.py) -----------------------
+// per CTA: [0] lifetime, [1] producer waiting for a free ring slot, [2] MMA thread waiting for A, [3] MMA thread waiting for a
+// free accumulator, [4] epilogue warp 2 waiting for an accumulator, [5] epilogue warp 2 inside epilogue_tile, [6] tiles
+__device__ long long g_gemm_prof[160 * 8];
+static int gemm_debug() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("B200_GEMM_DEBUG");
+        mode = e ? atoi(e) : 0;      // 1: counters; +2: A tiles loaded for the first row block only (no L2 traffic for A);
+    }                                //             +4: epilogue without global stores; +8: no epilogue work at all (ablations, wrong results)
+    return mode;
+}
+
 // ---- weight-stationary variant ---------------------------------------------------------------------
 // The streaming kernel above re-reads the B tile (BN x K weights, 196 KB at BN=256, K=384) from L2 for every 128 rows of
 // A: 294 KB of L2 traffic per tile made the LSTM input projection L2-bandwidth bound (~5.4 TB/s of L2 reads).  Here a
 // CTA is bound to ONE column block of B, loads it once into shared memory (<= 144 KB) and streams only A tiles through
 // a 3-stage ring: 98 KB of L2 traffic per tile.
-constexpr int WS_KB = 6;
-constexpr int WSC_DEFAULT_BN = 0, WSC_DEFAULT_CL = 0;   // multicast-cluster variant: off unless B200_GEMM_CLUSTER selects a shape  // K <= 384 fp16 (K <= 768 int8: a 128-byte row holds 64 halves or 128 bytes)
+constexpr int WS_KB = 6;             // K <= 384 fp16 (K <= 768 int8: a 128-byte row holds 64 halves or 128 bytes)
+constexpr int PAIR_DEFAULT = 1;      // cta_group::2 pair kernel for N % 256 == 0, K <= 384 (B200_GEMM_PAIR=0: off)
 
 // INT8 variant (I8 = 1; the reference's --quantize path runs koi's int8 LSTM, bonito/crf/model.py:245): A and B are int8 with
 // 128-element (128-byte) K blocks, tcgen05.mma kind::i8 accumulates s32 in tensor memory, the epilogue multiplies by a
@@ -373,8 +387,10 @@ template <int BN, int I8 = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep, int* __restrict__ ctr,
-               const float* __restrict__ col_scale) {
+               const float* __restrict__ col_scale, int prof) {
     using S = WsSmem<BN, I8>;
+    const long long t_start = prof ? clock64() : 0;
+    long long* pr = g_gemm_prof + (blockIdx.x % 160) * 8;
     constexpr int WS_STAGES = S::kStages;
     constexpr int KE = I8 ? 2 * BK : BK;          // K elements per 128-byte block
     extern __shared__ unsigned char smem_raw[];
@@ -428,18 +444,26 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             int stage = 0;
             uint32_t phase = 0;
+            long long w_empty = 0;
             for (int q = 0;; ++q) {
                 tq.publish(q, mb < m_blocks ? mb : -1);
                 if (mb >= m_blocks) break;
                 const int next = atomicAdd(&ctr[nb], 1);   // its latency hides behind the loads below
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    const long long t0 = prof ? clock64() : 0;
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    mbar_expect_tx(full_bar(stage), BM * BK * 2);
-                    tma_load_2d(base + S::kRing + stage * (BM * BK * 2), &map_a, full_bar(stage), kb * KE, mb * BM);
+                    if (prof) w_empty += clock64() - t0;
+                    if ((prof & 2) && q > 0) {
+                        mbar_arrive(full_bar(stage));      // ablation: the slot keeps the bytes it has
+                    } else {
+                        mbar_expect_tx(full_bar(stage), BM * BK * 2);
+                        tma_load_2d(base + S::kRing + stage * (BM * BK * 2), &map_a, full_bar(stage), kb * KE, mb * BM);
+                    }
                     if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
                 }
                 mb = next;
             }
+            if (prof) pr[1] = w_empty;
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -449,13 +473,18 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                       : tc_idesc_f16(BM, BN);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
+            long long w_full = 0, w_acc = 0;
             for (int q = 0; tq.take(q) >= 0; ++q) {
                 if (q == 0) mbar_wait(bres_bar, 0);
+                const long long t0 = prof ? clock64() : 0;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                if (prof) w_acc += clock64() - t0;
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    const long long t1 = prof ? clock64() : 0;
                     mbar_wait(full_bar(stage), phase);
+                    if (prof) w_full += clock64() - t1;
                     tc_fence_after();
                     const uint64_t adesc = tc_smem_desc_sw128(base + S::kRing + stage * (BM * BK * 2));
                     const uint64_t bdesc = tc_smem_desc_sw128(base + S::kBres + kb * (BN * 128));
@@ -470,12 +499,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tc_commit(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (prof) { pr[2] = w_full; pr[3] = w_acc; }
         }
     } else {
         // ===== epilogue warps =====
         const int quarter = warp & 3, ew = warp - 2, set = ew >> 2;
         unsigned char* tbuf = gen_base + S::kEpi + ew * 2048;
         __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + ew * 512);
+        long long w_tfull = 0, t_epi = 0, n_tiles = 0;
         stage_bias<BN>(sbias, ep.bias, nb, N, lane);       // the column block never changes
         float* sscale = nullptr;
         if (I8) {
@@ -488,183 +519,205 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int q = 0;; ++q) {
             const int mb = tq.take(q);
             if (mb < 0) break;
+            const long long t0 = prof ? clock64() : 0;
             mbar_wait(tfull_bar(acc), acc_phase);
+            const long long t1 = prof ? clock64() : 0;
             tc_fence_after();
-            epilogue_tile<BN, I8>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, set, lane, ep, sscale);
+            if (!(prof & 8))
+                epilogue_tile<BN, I8>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, (prof & 4) ? 0 : M, N, mb, nb, quarter, set,
+                                      lane, ep, sscale);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (prof) { w_tfull += t1 - t0; t_epi += clock64() - t1; ++n_tiles; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (prof && ew == 0 && lane == 0) { pr[4] = w_tfull; pr[5] = t_epi; pr[6] = n_tiles; }
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tc_dealloc(tmem_base, BN <= 128 ? 256 : 512);
     if (threadIdx.x == 0) release_tile_counters(ctr, n_blocks);
+    if (prof && threadIdx.x == 0) pr[0] = clock64() - t_start;
 }
 
 
-// ---- weight-stationary, A multicast across a cluster ------------------------------------------------------------------
-// The weight-stationary kernel above streams every 128 x K tile of A once PER COLUMN BLOCK (8 times for the LSTM input
-// projection at BN = 192) and can keep only 3 x 16 KB of A in flight next to its 144 KB of resident weights: per SM it needs
-// 42 B/clk of A at full tensor rate, and 48 KB in flight at ~1.5k cycles of loaded L2 latency deliver ~27 (measured: 0.62
-// of the cuBLAS rate).  Here CL CTAs of a cluster own CL ADJACENT column blocks and work on the SAME row block: each CTA
-// fetches 128/CL rows of every A stage and TMA-multicasts them into the ring of all CL CTAs (L2 reads of A divided by CL),
-// a ring slot is re-filled once the MMAs of all CL CTAs have drained it (tcgen05.commit multicast onto every CTA's
-// `empty` barrier, count CL), and BN = 128 halves the resident block, which pays for a 6-stage ring.  Row blocks are handed
-// out per cluster: rank 0 draws the ticket and posts it into every CTA's tile queue through distributed shared memory.
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n" ::
-            "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
-                 "h"(mask)
-                 : "memory");
-}
 __device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v) {
     asm volatile("st.shared::cluster.s32 [%0], %1;\n" ::"r"(cluster_addr), "r"(v) : "memory");
 }
 
-template <int BN>
-struct WcSmem {
-    static constexpr int kStages = BN <= 128 ? 6 : 3;
-    static constexpr uint32_t kBres = 0;                                  // [WS_KB][BN rows][128 B] SWIZZLE_128B
-    static constexpr uint32_t kRing = WS_KB * BN * 128;                   // kStages x (128 rows x 128 B)
+// ---- CTA pairs (cta_group::2): 256 x 256 tiles, the resident weight block split across the two SMs of a pair ---------------
+// scripts/gemm_profile.py: the weight-stationary kernel is bound by the bytes it moves through L2 -- ~4.6 KB/clk for the whole
+// chip, loads of A plus stores of C, whatever the mix (no stores: -1077 cycles per tile; no A loads: -380; neither: 2745 of a
+// 2304-cycle MMA floor) -- i.e. by 768/BN + 2 bytes per output element, and BN is capped by the shared memory the resident
+// block needs (192 columns = 144 KB).  A pair of SMs running tcgen05.mma.cta_group::2 shares ONE B operand: each CTA keeps 128
+// of the pair's 256 columns resident (96 KB), loads its own 128 rows of A, and the leader's M = 256 instructions read both
+// halves.  5 bytes per element instead of 6 (BN = 192) or 8 (BN = 128, the CRF head), half the operand bytes read from each
+// SM's shared memory per MMA, and a 6-stage ring.  Roles per CTA as above; only rank 0 issues MMAs, TMA loads of both CTAs
+// complete on rank 0's `full` barrier, tcgen05.commit multicasts `empty` / `tfull` to both CTAs, the epilogue warps of both
+// arrive on rank 0's `tempty`.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+            "r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {     // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+struct PairSmem {
+    static constexpr int kStages = 6;
+    static constexpr uint32_t kBres = 0;                                  // [WS_KB][128 rows][128 B]: this CTA's half of B
+    static constexpr uint32_t kRing = WS_KB * 128 * 128;                  // kStages x (128 rows x 128 B) of this CTA's A rows
     static constexpr uint32_t kEpi = kRing + kStages * BM * BK * 2;
     static constexpr uint32_t kBias = kEpi + EPI_WARPS * 2048;
     static constexpr uint32_t kBars = kBias + EPI_WARPS * 512;            // 2 * kStages + 6 mbarriers
-    static constexpr uint32_t kTileQ = kBars + 8 * (2 * kStages + 6);     // TQ mbarriers + TQ ints
+    static constexpr uint32_t kTileQ = kBars + 8 * (2 * kStages + 6);
     static constexpr uint32_t kTotal = kTileQ + 12 * TQ + 64 + 1024;
 };
+static_assert(PairSmem::kTotal <= SMEM_LIMIT, "pair kernel: shared memory");
 
-static_assert(WcSmem<192>::kTotal <= SMEM_LIMIT && WcSmem<128>::kTotal <= SMEM_LIMIT, "multicast kernel: shared memory");
-
-template <int BN, int CL>
+// A pair is bound to ONE 256-column block for its whole life and draws 256-row blocks from that block's ticket counter, like
+// the single-CTA kernel: the pairs of all column blocks then sweep over A at the same pace and every A tile comes from HBM
+// once and from L2 for the other column blocks.  (One global counter over column-block-major tiles keeps all 74 pairs busy
+// for any N, but re-reads the 655 MB of A from HBM once per column block: measured 806 vs 989 TFLOP/s.)
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_wsc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep, int* __restrict__ ctr) {
-    using S = WcSmem<BN>;
-    constexpr int ST = S::kStages;
-    constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
-    constexpr int SLICE_ROWS = BM / CL;
+gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep, int* __restrict__ ctr) {
+    using S = PairSmem;
+    constexpr int ST = S::kStages, BNP = 256;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + S::kBars;
-    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto full_bar = [&](int s) { return bars + 8u * s; };                 // used in rank 0 only
     auto empty_bar = [&](int s) { return bars + 8u * (ST + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * ST + s); };
-    auto tempty_bar = [&](int s) { return bars + 8u * (2 * ST + 2 + s); };
-    const uint32_t bres_bar = bars + 8u * (2 * ST + 4);
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * ST + 2 + s); }; // used in rank 0 only
+    const uint32_t bres_bar = bars + 8u * (2 * ST + 4);                    // used in rank 0 only
     const uint32_t tmem_slot = bars + 8u * (2 * ST + 5);
     unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t tq_bars = base + S::kTileQ, tq_tiles = base + S::kTileQ + 8 * TQ;
     volatile int* tq_tiles_gen = reinterpret_cast<volatile int*>(gen_base + S::kTileQ + 8 * TQ);
-    auto take = [&](int q) {   // the ticket was posted by rank 0 of the cluster (possibly this CTA) through shared::cluster
+    auto take = [&](int q) {
         mbar_wait_cluster(tq_bars + 8u * (uint32_t)(q & (TQ - 1)), (uint32_t)((q / TQ) & 1));
         return tq_tiles_gen[q & (TQ - 1)];
     };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, groups = n_blocks / CL;
+    const int m_blocks = (M + 2 * BM - 1) / (2 * BM), n_blocks = N / BNP;   // 256-row blocks, 256-column blocks
     const int k_blocks = (K + BK - 1) / BK;
-    const int grp = (int)(blockIdx.x / CL) % groups;      // column group of this cluster, for its whole life
-    const int nb = grp * CL + (int)rank;                  // this CTA's column block
+    const int nb = (int)(blockIdx.x / 2) % n_blocks;      // the pair's column block
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a));
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b));
         for (int s = 0; s < ST; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), CL);       // one tcgen05.commit per CTA of the cluster
+            mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), EPI_WARPS);
+            mbar_init(tempty_bar(s), 2 * EPI_WARPS);   // the epilogue warps of both CTAs
         }
         mbar_init(bres_bar, 1);
         for (int s = 0; s < TQ; ++s) mbar_init(tq_bars + 8u * s, 1);
         mbar_fence_init();
     }
-    if (warp == 1) tc_alloc(tmem_slot, BN <= 128 ? 256 : 512);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+    }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();      // every CTA's barriers exist before a peer's multicast or ticket can land
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + S::kBars + 8u * (2 * ST + 5));
 
     if (warp == 0) {
-        // ===== TMA producer: B once, then this CTA's slice of every A stage, multicast to the cluster =====
+        // ===== TMA producer (both CTAs): this CTA's half of the column block's B, then its 128 rows of every A stage =====
         if (elect_one_sync()) {
-            auto post = [&](int q, int tile) {     // rank 0: ticket -> every CTA's queue slot, then its barrier (release.cluster)
+            auto post = [&](int q, int tile) {
                 const uint32_t slot = (uint32_t)(q & (TQ - 1));
-                for (uint32_t r = 0; r < (uint32_t)CL; ++r) {
+                for (uint32_t r = 0; r < 2u; ++r) {
                     st_cluster_s32(mapa(tq_tiles + 4u * slot, r), tile);
                     mbar_arrive_remote(mapa(tq_bars + 8u * slot, r));
                 }
             };
+            const uint32_t l_bres = mapa(bres_bar, 0);
             int stage = 0;
             uint32_t phase = 0;
             int next = 0;
             if (rank == 0) {
-                const int first = atomicAdd(&ctr[grp], 1);
+                const int first = atomicAdd(&ctr[nb], 1);
                 post(0, first < m_blocks ? first : -1);
             }
             for (int q = 0;; ++q) {
                 const int mb = take(q);
                 if (mb < 0) break;
-                if (rank == 0) next = atomicAdd(&ctr[grp], 1);   // its latency hides behind the loads below
+                if (rank == 0) next = atomicAdd(&ctr[nb], 1);
                 if (q == 0) {
-                    mbar_expect_tx(bres_bar, (uint32_t)k_blocks * BN * 128);
+                    if (rank == 0) mbar_expect_tx(bres_bar, 2u * (uint32_t)k_blocks * 128 * 128);
                     for (int kb = 0; kb < k_blocks; ++kb)
-                        tma_load_2d(base + S::kBres + kb * (BN * 128), &map_b, bres_bar, kb * BK, nb * BN);
+                        tma_load_2d_pair(base + S::kBres + kb * (128 * 128), &map_b, l_bres, kb * BK, nb * BNP + (int)rank * 128);
                 }
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1);      // drained by the MMAs of all CL CTAs
-                    mbar_expect_tx(full_bar(stage), BM * BK * 2);
-                    tma_load_2d_mc(base + S::kRing + stage * (BM * BK * 2) + rank * (SLICE_ROWS * 128), &map_a, full_bar(stage),
-                                   kb * BK, mb * BM + (int)rank * SLICE_ROWS, MASK);
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * BM * BK * 2);
+                    tma_load_2d_pair(base + S::kRing + stage * (BM * BK * 2), &map_a, mapa(full_bar(stage), 0), kb * BK,
+                                     mb * 2 * BM + (int)rank * BM);
                     if (++stage == ST) { stage = 0; phase ^= 1; }
                 }
                 if (rank == 0) post(q + 1, next < m_blocks ? next : -1);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (elect_one_sync()) {
-            const uint32_t idesc = tc_idesc_f16(BM, BN);
+        // ===== MMA issuer: rank 0 only, M = 256 across the pair =====
+        if (rank == 0 && elect_one_sync()) {
+            const uint32_t idesc = tc_idesc_f16(2 * BM, BNP);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int q = 0; take(q) >= 0; ++q) {
-                if (q == 0) mbar_wait(bres_bar, 0);
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                if (q == 0) mbar_wait_cluster(bres_bar, 0);      // both halves of the column block have landed
+                mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BNP);
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
+                    mbar_wait_cluster(full_bar(stage), phase);
                     tc_fence_after();
                     const uint64_t adesc = tc_smem_desc_sw128(base + S::kRing + stage * (BM * BK * 2));
-                    const uint64_t bdesc = tc_smem_desc_sw128(base + S::kBres + kb * (BN * 128));
+                    const uint64_t bdesc = tc_smem_desc_sw128(base + S::kBres + kb * (128 * 128));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        tc_mma_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc_commit_mc(empty_bar(stage), MASK);        // this CTA is done with the slot: tell every producer
+                        tc_mma_ss_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_pair(empty_bar(stage));
                     if (++stage == ST) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull_bar(acc));
+                tc_commit_pair(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ===== epilogue warps =====
+        // ===== epilogue warps (both CTAs): this CTA's 128 rows of the pair's tile =====
         const int quarter = warp & 3, ew = warp - 2, set = ew >> 2;
         unsigned char* tbuf = gen_base + S::kEpi + ew * 2048;
         __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + ew * 512);
-        stage_bias<BN>(sbias, ep.bias, nb, N, lane);
+        const uint32_t l_tempty0 = mapa(tempty_bar(0), 0), l_tempty1 = mapa(tempty_bar(1), 0);
+        stage_bias<BNP>(sbias, ep.bias, nb, N, lane);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int q = 0;; ++q) {
@@ -672,19 +725,20 @@ gemm_wsc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (mb < 0) break;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            epilogue_tile<BN, 0>(tmem_base + (uint32_t)(acc * BN), tbuf, sbias, C, ldc, M, N, mb, nb, quarter, set, lane, ep);
+            epilogue_tile<BNP, 0>(tmem_base + (uint32_t)(acc * BNP), tbuf, sbias, C, ldc, M, N, mb * 2 + (int)rank, nb, quarter, set,
+                                  lane, ep);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) mbar_arrive_remote(acc ? l_tempty1 : l_tempty0);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc_dealloc(tmem_base, BN <= 128 ? 256 : 512);
-    cluster_sync_all();      // nobody leaves while a peer's commit may still arrive on this CTA's barriers
-    if (threadIdx.x == 0) release_tile_counters(ctr, groups);
+    cluster_sync_all();      // both CTAs are done with the pair's tensor memory and barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
+    if (threadIdx.x == 0) release_tile_counters(ctr, n_blocks);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -803,66 +857,59 @@ int launch_ws(const void* A, long long lda, const void* B, __half* C, long long 
     int* ctr = nullptr;
     rc = take_counters(n_blocks + 1, stream, &ctr);
     if (rc) return rc;
-    kern<<<per_block * n_blocks, THREADS, WsSmem<BN, I8>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep, ctr, col_scale);
+    kern<<<per_block * n_blocks, THREADS, WsSmem<BN, I8>::kTotal, stream>>>(map_a, map_b, C, ldc, M, N, K, ep, ctr, col_scale, gemm_debug());
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-// cluster shape of the multicast kernel: B200_GEMM_CLUSTER = "<BN>x<CL>" (128x2, 128x4, 192x2, 192x4) or "0" (off)
-static void cluster_shape(int* bn, int* cl) {
-    static int s_bn = -1, s_cl = 0;
-    if (s_bn < 0) {
-        int b = WSC_DEFAULT_BN, c = WSC_DEFAULT_CL;
-        const char* e = getenv("B200_GEMM_CLUSTER");
-        if (e && e[0] == '0') b = c = 0;
-        else if (e && sscanf(e, "%dx%d", &b, &c) != 2) { b = WSC_DEFAULT_BN; c = WSC_DEFAULT_CL; }
-        s_cl = c;
-        s_bn = b;
+static int pair_enabled() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("B200_GEMM_PAIR");
+        mode = e ? atoi(e) : PAIR_DEFAULT;
     }
-    *bn = s_bn;
-    *cl = s_cl;
+    return mode;
 }
 
-template <int BN, int CL>
-int launch_wsc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
-               const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
+int launch_pair(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
+                const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
     CUtensorMap map_a, map_b;
-    int rc = make_map(&map_a, A, M, K, lda, BM / CL);
+    int rc = make_map(&map_a, A, M, K, lda, BM);
     if (rc) return rc;
-    rc = make_map(&map_b, B, N, K, K, BN);
+    rc = make_map(&map_b, B, N, K, K, 128);
     if (rc) return rc;
-    auto kern = gemm_wsc_kernel<BN, CL>;
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WcSmem<BN>::kTotal));
+    auto kern = gemm_pair_kernel;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairSmem::kTotal));
     int dev = 0, sms = 0;
     B200_CHECK_CUDA(cudaGetDevice(&dev));
     B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
-    const int m_blocks = (M + BM - 1) / BM, groups = N / BN / CL;
+    const int m_blocks = (M + 2 * BM - 1) / (2 * BM), n_blocks = N / 256;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = WcSmem<BN>::kTotal;
+    cfg.dynamicSmemBytes = PairSmem::kTotal;
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static int s_max_clusters = 0;             // per (BN, CL) instantiation: co-resident clusters on an idle device
-    if (s_max_clusters == 0) {
-        cfg.gridDim = dim3(CL * 64);
+    static int s_max_pairs = 0;
+    if (s_max_pairs == 0) {
+        cfg.gridDim = dim3(2 * 128);
         int n = 0;
         B200_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-        s_max_clusters = n > 0 ? n : 1;
+        s_max_pairs = n > 0 ? n : 1;
     }
-    int clusters = sms / CL < s_max_clusters ? sms / CL : s_max_clusters;
-    int per_group = clusters / groups;
-    if (per_group > m_blocks) per_group = m_blocks;
-    if (per_group < 1) per_group = 1;
-    cfg.gridDim = dim3(per_group * groups * CL);
+    int pairs = sms / 2 < s_max_pairs ? sms / 2 : s_max_pairs;
+    int per_block = pairs / n_blocks;
+    if (per_block > m_blocks) per_block = m_blocks;
+    if (per_block < 1) per_block = 1;
+    cfg.gridDim = dim3(per_block * n_blocks * 2);
     int* ctr = nullptr;
-    rc = take_counters(groups + 1, stream, &ctr);
+    rc = take_counters(n_blocks + 1, stream, &ctr);
     if (rc) return rc;
     B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, C, ldc, M, N, K, ep, ctr));
     return 0;
@@ -876,14 +923,8 @@ int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, l
                  "gemm_tc: operands must be 16-byte aligned");
     const char* env = getenv("B200_GEMM_WS");
     const bool ws_ok = !(env && env[0] == '0') && K <= WS_KB * BK && M >= 4 * BM;
-    int cbn = 0, ccl = 0;
-    cluster_shape(&cbn, &ccl);
-    if (ws_ok && ccl > 1 && M >= 64 * BM && N % (cbn * ccl) == 0 && N / cbn <= 64) {
-        if (cbn == 128 && ccl == 2) return launch_wsc<128, 2>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
-        if (cbn == 128 && ccl == 4) return launch_wsc<128, 4>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
-        if (cbn == 192 && ccl == 2) return launch_wsc<192, 2>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
-        if (cbn == 192 && ccl == 4) return launch_wsc<192, 4>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
-    }
+    if (ws_ok && pair_enabled() && M >= 64 * BM && N % 256 == 0 && N / 256 <= 64 && ep.act != B200_ACT_SWIGLU)
+        return launch_pair(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     if (ws_ok && N % 192 == 0 && N / 192 <= 64) return launch_ws<192, 0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     if (ws_ok && N % 128 == 0 && N / 128 <= 64) return launch_ws<128, 0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     if (N % 256 == 0) return launch_tc<256>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
@@ -901,4 +942,11 @@ int launch_gemm_i8(const int8_t* A, long long lda, const int8_t* B, const float*
     if (N % 192 == 0 && N / 192 <= 64) return launch_ws<192, 1>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream, col_scale);
     B200_REQUIRE(N % 128 == 0 && N / 128 <= 64, "gemm_i8: N (%d) must be a multiple of 192 or 128", N);
     return launch_ws<128, 1>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream, col_scale);
+}
+
+// copies the per-CTA cycle counters of the last weight-stationary launch (B200_GEMM_DEBUG=1): 160 x 8 values
+int copy_gemm_profile(long long* host_out) {
+    B200_CHECK_CUDA(cudaDeviceSynchronize());
+    B200_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_gemm_prof, sizeof(long long) * 160 * 8));
+    return 0;
 }

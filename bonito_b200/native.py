@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200_lstm_rec_tile_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_debug_lstm_tile_timeline": (c_int, [c_void_p, c_int]),
     "b200_debug_attention_timeline": (c_int, [c_void_p, c_int]),
+    "b200_debug_gemm_profile": (c_int, [c_void_p]),
     "b200_debug_tmem_probe": (c_int, [c_void_p, c_void_p]),
     "b200_debug_lstm_timeline": (c_int, [c_void_p, c_int]),
     "b200_debug_lstm_max_clusters": (c_int, []),

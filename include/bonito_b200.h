@@ -130,6 +130,8 @@ int b200_lstm_rec_tile_fwd(const void* gx, const void* whh, void* y, void* works
 /* Timing aid: after a b200_attention_fwd launched with B200_ATTN_DEBUG=1, the SM-clock stamps CTA 0 recorded for its first
  * query tiles ([tile][16] int64, HOST buffer; see attention_tc.cu).  Returns the number of tiles copied (<= 64). */
 int b200_debug_attention_timeline(long long* host_out, int max_tiles);
+/* B200_GEMM_DEBUG=1: per-CTA cycle counters of the last weight-stationary GEMM launch, 160 x 8 values (gemm_tc.cu) */
+int b200_debug_gemm_profile(long long* host_out);
 
 /* Timing aid: as b200_debug_lstm_timeline, for b200_lstm_rec_tile_fwd. */
 int b200_debug_lstm_tile_timeline(long long* host_out, int max_steps);
