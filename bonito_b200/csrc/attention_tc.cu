@@ -331,6 +331,273 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restr
     if (warp == SM_WARPS) tc_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ---- second version: sixteen softmax warps, one output accumulator ------------------------------------------------------
+// The kernel above spends ~10 k cycles per query tile against ~1.5 k of tensor work: each of its eight softmax warps walks
+// through load -> max -> exchange -> exp -> store three times per tile with nothing to overlap, the three partial outputs are
+// read back and combined in registers, and the next tile's Q K^T cannot start before that has happened (S_j and O_j share
+// columns).  Here
+//   * the row maximum is taken over the WHOLE band first (pass 1 reads S_0..S_2, one exchange per tile), so all three
+//     P_j V_j products accumulate into ONE 64-column O: a third of the read-back, no rescaling, and O has its own columns
+//     [384, 448): the next tile's Q K^T is issued as soon as this tile's MMAs have completed, while the softmax warps are
+//     still writing this tile's output;
+//   * the row sums come from the tensor core as well: P_j times a 128 x 16 block of ones accumulates into columns
+//     [448, 464) -- exactly the sum of the fp16 probabilities the P V product sees, no unpack / add per element, no second
+//     exchange;
+//   * sixteen softmax warps, four per TMEM lane quarter, 32 of a key tile's 128 columns each (four warps per scheduler
+//     instead of two); warp c keeps its P in the first 16 of ITS OWN 32 columns of S_j, so no warp overwrites scores another
+//     one has yet to read in pass 2.
+namespace v2 {
+
+constexpr int SM_WARPS = 16, CSPLIT = 4;
+constexpr int THREADS = (SM_WARPS + 1) * 32;
+constexpr uint32_t OFF_XCH = OFF_BARS + 256;                             // float [2][CSPLIT][BQ] row maxima
+constexpr uint32_t OFF_ONES = (OFF_XCH + 2 * CSPLIT * BQ * 4 + 1023u) & ~1023u;   // 16 rows x 128 B of fp16 ones (B operand of the row sums)
+constexpr uint32_t SMEM_BYTES = OFF_ONES + 2048 + 1024;
+constexpr uint32_t COL_O = 384, COL_L = 448;
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restrict__ out, int N, int T, int NH, int wl,
+                     int wr, float scale_log2e, int debug) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
+    AttnBars bars;
+    bars.base = base + OFF_BARS;
+    const uint32_t tmem_slot = bars.base + 112;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nqt = (T + BQ - 1) / BQ;
+    const int items = N * NH;
+    const bool tl = debug != 0 && blockIdx.x == 0;
+#define ATL(it_, k_) do { if (tl && (it_) < ATL_TILES) g_attn_timeline[(it_)][(k_)] = clock64(); } while (0)
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_qkv));
+        for (int b = 0; b < 2; ++b) mbar_init(bars.qfull(b), 1);
+        for (int sl = 0; sl < RING; ++sl) mbar_init(bars.kvfull(sl), 1);
+        for (int j = 0; j < NKT; ++j) mbar_init(bars.s(j), 1);
+        mbar_init(bars.p(0), SM_WARPS);            // one arrive per softmax warp, after all three P_j
+        mbar_init(bars.o(), 1);
+        mbar_init(bars.tfree(), SM_WARPS);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 512; i += THREADS) reinterpret_cast<uint32_t*>(gbase + OFF_ONES)[i] = 0x3C003C00u;   // fp16 1.0 pairs
+    fence_proxy_async_smem();
+    if (warp == SM_WARPS) tc_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 112);
+
+    if (warp == SM_WARPS) {
+        // ===== TMA producer + MMA issuer (one thread) =====
+        if (elect_one_sync()) {
+            constexpr uint32_t idesc_s = tc_idesc_f16(BQ, BKV);
+            constexpr uint32_t idesc_o = tc_idesc_f16(BQ, HD) | (1u << 16);   // bit 16: B (V) is MN-major
+            constexpr uint32_t idesc_l = tc_idesc_f16(BQ, 16);               // B = ones, K-major
+            const uint64_t ones_desc = tc_smem_desc_sw128(base + OFF_ONES);
+            int it = 0, kl_issued = 0, q_issued = 0, kl_released = 0;
+            const int my_items = blockIdx.x < items ? (items - blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            const int total_q = my_items * nqt, total_k = my_items * (nqt + 2);
+
+            auto issue_loads = [&]() {
+                while (kl_issued < total_k && kl_issued < kl_released + RING) {
+                    const int li = kl_issued / (nqt + 2), kt = kl_issued % (nqt + 2) - 1;
+                    const int item = blockIdx.x + li * (int)gridDim.x, n = item / NH, h = item % NH;
+                    const int sl = kl_issued & (RING - 1);
+                    mbar_expect_tx(bars.kvfull(sl), 2 * TILE_BYTES);
+                    tma_load_3d(base + OFF_K + sl * TILE_BYTES, &map_qkv, bars.kvfull(sl), NH * HD + h * HD, kt * BKV, n);
+                    tma_load_3d(base + OFF_V + sl * TILE_BYTES, &map_qkv, bars.kvfull(sl), 2 * NH * HD + h * HD, kt * BKV, n);
+                    ++kl_issued;
+                }
+                while (q_issued < total_q && q_issued < it + 2) {
+                    const int li = q_issued / nqt, qt = q_issued % nqt;
+                    const int item = blockIdx.x + li * (int)gridDim.x, n = item / NH, h = item % NH;
+                    mbar_expect_tx(bars.qfull(q_issued & 1), TILE_BYTES);
+                    tma_load_3d(base + OFF_Q + (q_issued & 1) * TILE_BYTES, &map_qkv, bars.qfull(q_issued & 1), h * HD, qt * BQ, n);
+                    ++q_issued;
+                }
+            };
+
+            issue_loads();
+            for (int li = 0; li < my_items; ++li) {
+                const int first_kl = li * (nqt + 2);
+                for (int qt = 0; qt < nqt; ++qt, ++it) {
+                    // S_j = Q K_j^T: the previous tile's MMAs have completed (wait on o() below), so S / P are free
+                    mbar_wait(bars.qfull(it & 1), (uint32_t)((it >> 1) & 1));
+                    tc_fence_after();
+                    ATL(it, 0);
+                    const uint64_t qdesc = tc_smem_desc_sw128(base + OFF_Q + (it & 1) * TILE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < NKT; ++j) {
+                        const int kl = first_kl + qt + j, sl = kl & (RING - 1);
+                        mbar_wait(bars.kvfull(sl), (uint32_t)((kl / RING) & 1));
+                        tc_fence_after();
+                        const uint64_t kdesc = tc_smem_desc_sw128(base + OFF_K + sl * TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < HD / 16; ++k)
+                            tc_mma_ss(tmem_base + (uint32_t)(j * 128), qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+                        tc_commit(bars.s(j));
+                    }
+                    ATL(it, 1);
+                    // the loads the previous tile's completion made room for: off the critical path (the softmax warps are busy
+                    // with S for the next few thousand cycles; the ring holds this tile's keys and the next one's already)
+                    issue_loads();
+                    ATL(it, 4);
+                    // O += P_j V_j and L += P_j 1: P of keys [32 c, 32 c + 32) sits in columns [32 c, 32 c + 16) of S_j
+                    mbar_wait(bars.p(0), (uint32_t)(it & 1));
+                    if (it > 0) mbar_wait(bars.tfree(), (uint32_t)((it - 1) & 1));    // the previous tile's O / L have been read
+                    tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < NKT; ++j) {
+                        const int kl = first_kl + qt + j, sl = kl & (RING - 1);
+                        const uint64_t vdesc = tc_smem_desc_sw128(base + OFF_V + sl * TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BKV / 16; ++k) {
+                            const uint32_t a = tmem_base + (uint32_t)(j * 128 + (k >> 1) * 32 + (k & 1) * 8);
+                            tc_mma_ts(tmem_base + COL_O, a, vdesc + (uint64_t)(k * (2048 >> 4)), idesc_o, (j | k) != 0 ? 1u : 0u);
+                            tc_mma_ts(tmem_base + COL_L, a, ones_desc, idesc_l, (j | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(bars.o());
+                    ATL(it, 2);
+                    mbar_wait(bars.o(), (uint32_t)(it & 1));
+                    ATL(it, 3);
+                    kl_released = first_kl + (qt + 1 < nqt ? qt + 1 : nqt + 2);
+                    if (qt + 1 == nqt) issue_loads();      // the next item's first key tiles: nothing else can load them in time
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== softmax warps: row r = 32 quarter + lane; warp c = warp / 4 takes columns [32 c, 32 c + 32) of every key tile =====
+        const int quarter = warp & 3, cq = warp >> 2;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* xch = reinterpret_cast<float*>(gbase + OFF_XCH);      // [parity][c][row]
+        constexpr uint32_t NEG_INF = 0xff800000u;
+        int it = 0;
+        for (int item = blockIdx.x; item < items; item += (int)gridDim.x) {
+            const int n = item / NH, h = item % NH;
+            for (int qt = 0; qt < nqt; ++qt, ++it) {
+                const int q0 = qt * BQ, q = q0 + r, k0 = q0 - BKV;
+                const int lo = max(BKV + r - wl, -k0), hi = min(BKV + r + wr, T - 1 - k0);   // visible band columns (0 .. 383)
+                const uint32_t ph = (uint32_t)(it & 1);
+                // ---- pass 1: row maximum over the visible part of this warp's 3 x 32 columns ----
+                float mx = -1e30f;       // (finite floor: a fully masked row stays well defined)
+                int kinds = 0;           // 2 bits per key tile: 0 = no lane of the warp sees the piece, 2 = all see all of it, 1 = mixed
+#pragma unroll 1
+                for (int j = 0; j < NKT; ++j) {
+                    const int a = max(lo - j * BKV - cq * 32, 0), b = min(hi - j * BKV - cq * 32, 31);
+                    const bool any = __any_sync(0xffffffffu, a <= b);
+                    const bool all = __all_sync(0xffffffffu, a == 0 && b == 31);
+                    const int kind = all ? 2 : (any ? 1 : 0);
+                    kinds |= kind << (2 * j);
+                    mbar_wait(bars.s(j), ph);
+                    if (warp == 0 && lane == 0 && j == 0) ATL(it, 5);
+                    if (kind == 0) continue;
+                    tc_fence_after();
+                    uint32_t s[32];
+                    tc_ld_32x32b_x32(lane_addr + (uint32_t)(j * 128 + cq * 32), s);
+                    tc_wait_ld();
+                    float m0 = -1e30f, m1 = -1e30f, m2 = -1e30f, m3 = -1e30f;
+                    if (kind == 2) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            m0 = fmaxf(m0, __uint_as_float(s[c]));
+                            m1 = fmaxf(m1, __uint_as_float(s[c + 1]));
+                            m2 = fmaxf(m2, __uint_as_float(s[c + 2]));
+                            m3 = fmaxf(m3, __uint_as_float(s[c + 3]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            m0 = fmaxf(m0, (c >= a && c <= b) ? __uint_as_float(s[c]) : -1e30f);
+                            m1 = fmaxf(m1, (c + 1 >= a && c + 1 <= b) ? __uint_as_float(s[c + 1]) : -1e30f);
+                            m2 = fmaxf(m2, (c + 2 >= a && c + 2 <= b) ? __uint_as_float(s[c + 2]) : -1e30f);
+                            m3 = fmaxf(m3, (c + 3 >= a && c + 3 <= b) ? __uint_as_float(s[c + 3]) : -1e30f);
+                        }
+                    }
+                    mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                }
+                if (warp == 0 && lane == 0) ATL(it, 6);
+                xch[((int)ph * CSPLIT + cq) * BQ + r] = mx;
+                asm volatile("bar.sync %0, 128;\n" ::"r"(1 + quarter) : "memory");    // the four warps of this lane quarter
+#pragma unroll
+                for (int c = 0; c < CSPLIT; ++c) mx = fmaxf(mx, xch[((int)ph * CSPLIT + c) * BQ + r]);
+                if (warp == 0 && lane == 0) ATL(it, 7);
+                const float mb = mx * scale_log2e;
+                // ---- pass 2: P = 2^(s * scale - m), fp16 pairs, into the first 16 of this warp's own columns ----
+#pragma unroll 1
+                for (int j = 0; j < NKT; ++j) {
+                    const int kind = (kinds >> (2 * j)) & 3;
+                    uint32_t pk[16];
+                    if (kind != 0) {
+                        const int a = max(lo - j * BKV - cq * 32, 0), b = min(hi - j * BKV - cq * 32, 31);
+                        uint32_t s[32];
+                        tc_ld_32x32b_x32(lane_addr + (uint32_t)(j * 128 + cq * 32), s);
+                        tc_wait_ld();
+                        if (kind == 1) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) s[c] = (c >= a && c <= b) ? s[c] : NEG_INF;    // 2^-inf = 0
+                        }
+#pragma unroll
+                        for (int c2 = 0; c2 < 16; ++c2) {
+                            // arguments (<= 0) rounded to fp16 -- P is stored as fp16 anyway -- two exponentials per MUFU operation
+                            const __half2 x2 = __floats2half2_rn(fmaf(__uint_as_float(s[2 * c2]), scale_log2e, -mb),
+                                                                 fmaf(__uint_as_float(s[2 * c2 + 1]), scale_log2e, -mb));
+                            asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[c2]) : "r"(*reinterpret_cast<const uint32_t*>(&x2)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int c2 = 0; c2 < 16; ++c2) pk[c2] = 0u;
+                    }
+                    tc_st_32x32b_x16(lane_addr + (uint32_t)(j * 128 + cq * 32), pk);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars.p(0));
+                if (warp == 0 && lane == 0) ATL(it, 8);
+                // ---- epilogue: out[q][16 c .. 16 c + 16) of this head = O / L ----
+                mbar_wait(bars.o(), ph);
+                tc_fence_after();
+                if (warp == 0 && lane == 0) ATL(it, 12);
+                uint32_t o[16], lsum;
+                tc_ld_32x32b_x16(lane_addr + COL_O + (uint32_t)(cq * 16), o);
+                tc_ld_32x32b_x1(lane_addr + COL_L, lsum);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars.tfree());
+                if (warp == 0 && lane == 0) ATL(it, 13);
+                if (q < T) {
+                    const float L = __uint_as_float(lsum);
+                    const float inv = L > 0.f ? 1.0f / L : 0.f;
+                    __half* dst = out + ((size_t)n * T + q) * (size_t)(NH * HD) + h * HD + cq * 16;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        __half2 hh[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+                            hh[p] = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * p]) * inv, __uint_as_float(o[g * 8 + 2 * p + 1]) * inv);
+                        *reinterpret_cast<uint4*>(dst + g * 8) = *reinterpret_cast<const uint4*>(hh);
+                    }
+                }
+                if (warp == 0 && lane == 0) ATL(it, 14);
+            }
+        }
+    }
+#undef ATL
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == SM_WARPS) tc_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace v2
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -375,7 +642,18 @@ int launch_attention_tc(const __half* qkv, __half* out, int N, int T, int NH, in
     const int grid = items < sms ? items : sms;
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
     const char* dbg = getenv("B200_ATTN_DEBUG");
-    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map, out, N, T, NH, wl, wr, scale_log2e, dbg ? atoi(dbg) : 0);
+    static int version = 0;     // B200_ATTN_TC=1: the first version (eight softmax warps, per-key-tile maxima)
+    if (version == 0) {
+        const char* e = getenv("B200_ATTN_TC");
+        version = (e && e[0] == '1') ? 1 : 2;
+    }
+    if (version == 1) {
+        attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map, out, N, T, NH, wl, wr, scale_log2e, dbg ? atoi(dbg) : 0);
+    } else {
+        B200_CHECK_CUDA(cudaFuncSetAttribute(v2::attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::SMEM_BYTES));
+        v2::attention_tc2_kernel<<<grid, v2::THREADS, v2::SMEM_BYTES, stream>>>(map, out, N, T, NH, wl, wr, scale_log2e,
+                                                                                 dbg ? atoi(dbg) : 0);
+    }
     B200_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

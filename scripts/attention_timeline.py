@@ -19,10 +19,16 @@ print("rotary + attention: %.3f ms" % e0.elapsed_time(e1))
 buf = np.zeros((64, 16), dtype=np.int64)
 n = native.load().b200_debug_attention_timeline(buf.ctypes.data_as(ctypes.c_void_p), 64)
 tl = buf[:n].astype(np.float64)
-names = ["mma: Q+tmem ready", "mma: QK issued", "mma: PV issued", "mma: O complete", "mma: loads issued", "sm: s(0) seen", "sm: S0 loaded",
-         "sm: max exchanged", "sm: P0 arrived", "sm: s(1) seen", "sm: P1 arrived", "sm: P2 arrived", "sm: o seen", "sm: O loaded", "sm: out stored"]
+if os.environ.get("B200_ATTN_TC") == "1":
+    names = ["mma: Q+tmem ready", "mma: QK issued", "mma: PV issued", "mma: O complete", "mma: loads issued", "sm: s(0) seen", "sm: S0 loaded",
+             "sm: max exchanged", "sm: P0 arrived", "sm: s(1) seen", "sm: P1 arrived", "sm: P2 arrived", "sm: o seen", "sm: O loaded", "sm: out stored"]
+else:    # second version: one pass for the maxima, one for the probabilities
+    names = ["mma: Q ready", "mma: QK issued", "mma: PV issued", "mma: O complete", "mma: loads issued", "sm: s(0) seen", "sm: pass 1 done",
+             "sm: max exchanged", "sm: P arrived", None, None, None, "sm: o seen", "sm: O loaded", "sm: out stored"]
 sel = slice(10, 50)
 base = tl[sel, 0]
 print("cycles per tile: %.0f" % np.diff(tl[sel, 0]).mean())
 for i, nm in enumerate(names):
+    if nm is None:
+        continue
     print("%-22s +%7.0f" % (nm, (tl[sel, i] - base).mean()))
