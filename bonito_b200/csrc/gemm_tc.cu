@@ -595,11 +595,18 @@ static_assert(PairSmem::kTotal <= SMEM_LIMIT, "pair kernel: shared memory");
 // the single-CTA kernel: the pairs of all column blocks then sweep over A at the same pace and every A tile comes from HBM
 // once and from L2 for the other column blocks.  (One global counter over column-block-major tiles keeps all 74 pairs busy
 // for any N, but re-reads the 655 MB of A from HBM once per column block: measured 806 vs 989 TFLOP/s.)
+// RES = 1: weight-stationary (above).  RES = 0: both operands streamed -- a stage holds this CTA's 128 rows of A and its 128
+// of the tile's 256 rows of B (32 KB, 6 stages), tiles come from ONE ticket counter with the column block fastest (the pairs
+// work on a few row blocks of A at a time, across all column blocks: A and the weights are re-read from L2), any K.  Used by
+// the transformer's fc2 (K = 2048) instead of the single-CTA streaming kernel.
+template <int RES>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  __half* __restrict__ C, long long ldc, int M, int N, int K, GemmEpilogue ep, int* __restrict__ ctr) {
     using S = PairSmem;
     constexpr int ST = S::kStages, BNP = 256;
+    constexpr uint32_t STAGE = RES ? BM * BK * 2 : 2 * BM * BK * 2;      // bytes per ring stage of one CTA
+    constexpr uint32_t RING0 = RES ? S::kRing : 0;                        // the ring takes the resident block's place when streaming
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + S::kBars;
@@ -621,7 +628,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t rank = cluster_ctarank();
     const int m_blocks = (M + 2 * BM - 1) / (2 * BM), n_blocks = N / BNP;   // 256-row blocks, 256-column blocks
     const int k_blocks = (K + BK - 1) / BK;
-    const int nb = (int)(blockIdx.x / 2) % n_blocks;      // the pair's column block
+    const int nb_fixed = (int)(blockIdx.x / 2) % n_blocks;    // RES: the pair's column block
+    const int tickets = RES ? m_blocks : m_blocks * n_blocks;
+    int* my_ctr = RES ? ctr + nb_fixed : ctr;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a));
@@ -649,7 +658,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + S::kBars + 8u * (2 * ST + 5));
 
     if (warp == 0) {
-        // ===== TMA producer (both CTAs): this CTA's half of the column block's B, then its 128 rows of every A stage =====
+        // ===== TMA producer (both CTAs) =====
         if (elect_one_sync()) {
             auto post = [&](int q, int tile) {
                 const uint32_t slot = (uint32_t)(q & (TQ - 1));
@@ -663,26 +672,29 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t phase = 0;
             int next = 0;
             if (rank == 0) {
-                const int first = atomicAdd(&ctr[nb], 1);
-                post(0, first < m_blocks ? first : -1);
+                const int first = atomicAdd(my_ctr, 1);
+                post(0, first < tickets ? first : -1);
             }
             for (int q = 0;; ++q) {
-                const int mb = take(q);
-                if (mb < 0) break;
-                if (rank == 0) next = atomicAdd(&ctr[nb], 1);
-                if (q == 0) {
+                const int tile = take(q);
+                if (tile < 0) break;
+                if (rank == 0) next = atomicAdd(my_ctr, 1);
+                const int mb = RES ? tile : tile / n_blocks, nb = RES ? nb_fixed : tile - mb * n_blocks;
+                if (RES && q == 0) {
                     if (rank == 0) mbar_expect_tx(bres_bar, 2u * (uint32_t)k_blocks * 128 * 128);
                     for (int kb = 0; kb < k_blocks; ++kb)
                         tma_load_2d_pair(base + S::kBres + kb * (128 * 128), &map_b, l_bres, kb * BK, nb * BNP + (int)rank * 128);
                 }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * BM * BK * 2);
-                    tma_load_2d_pair(base + S::kRing + stage * (BM * BK * 2), &map_a, mapa(full_bar(stage), 0), kb * BK,
-                                     mb * 2 * BM + (int)rank * BM);
+                    const uint32_t l_full = mapa(full_bar(stage), 0);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * STAGE);
+                    tma_load_2d_pair(base + RING0 + stage * STAGE, &map_a, l_full, kb * BK, mb * 2 * BM + (int)rank * BM);
+                    if (!RES)
+                        tma_load_2d_pair(base + RING0 + stage * STAGE + BM * BK * 2, &map_b, l_full, kb * BK, nb * BNP + (int)rank * 128);
                     if (++stage == ST) { stage = 0; phase ^= 1; }
                 }
-                if (rank == 0) post(q + 1, next < m_blocks ? next : -1);
+                if (rank == 0) post(q + 1, next < tickets ? next : -1);
             }
         }
     } else if (warp == 1) {
@@ -692,15 +704,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int q = 0; take(q) >= 0; ++q) {
-                if (q == 0) mbar_wait_cluster(bres_bar, 0);      // both halves of the column block have landed
+                if (RES && q == 0) mbar_wait_cluster(bres_bar, 0);      // both halves of the column block have landed
                 mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BNP);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait_cluster(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint64_t adesc = tc_smem_desc_sw128(base + S::kRing + stage * (BM * BK * 2));
-                    const uint64_t bdesc = tc_smem_desc_sw128(base + S::kBres + kb * (128 * 128));
+                    const uint64_t adesc = tc_smem_desc_sw128(base + RING0 + stage * STAGE);
+                    const uint64_t bdesc = tc_smem_desc_sw128(RES ? base + S::kBres + kb * (128 * 128)
+                                                                  : base + RING0 + stage * STAGE + BM * BK * 2);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
                         tc_mma_ss_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -717,12 +730,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         unsigned char* tbuf = gen_base + S::kEpi + ew * 2048;
         __half* sbias = reinterpret_cast<__half*>(gen_base + S::kBias + ew * 512);
         const uint32_t l_tempty0 = mapa(tempty_bar(0), 0), l_tempty1 = mapa(tempty_bar(1), 0);
-        stage_bias<BNP>(sbias, ep.bias, nb, N, lane);
-        int acc = 0;
+        int acc = 0, cur_nb = -1;
         uint32_t acc_phase = 0;
         for (int q = 0;; ++q) {
-            const int mb = take(q);
-            if (mb < 0) break;
+            const int tile = take(q);
+            if (tile < 0) break;
+            const int mb = RES ? tile : tile / n_blocks, nb = RES ? nb_fixed : tile - mb * n_blocks;
+            if (nb != cur_nb) {      // before the wait: its latency hides behind the mainloop
+                stage_bias<BNP>(sbias, ep.bias, nb, N, lane);
+                cur_nb = nb;
+            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             epilogue_tile<BNP, 0>(tmem_base + (uint32_t)(acc * BNP), tbuf, sbias, C, ldc, M, N, mb * 2 + (int)rank, nb, quarter, set,
@@ -738,7 +755,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     cluster_sync_all();      // both CTAs are done with the pair's tensor memory and barriers
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
-    if (threadIdx.x == 0) release_tile_counters(ctr, n_blocks);
+    if (threadIdx.x == 0) release_tile_counters(ctr, RES ? n_blocks : 1);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -871,6 +888,7 @@ static int pair_enabled() {
     return mode;
 }
 
+template <int RES>
 int launch_pair(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
                 const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
     CUtensorMap map_a, map_b;
@@ -878,7 +896,7 @@ int launch_pair(const __half* A, long long lda, const __half* B, __half* C, long
     if (rc) return rc;
     rc = make_map(&map_b, B, N, K, K, 128);
     if (rc) return rc;
-    auto kern = gemm_pair_kernel;
+    auto kern = gemm_pair_kernel<RES>;
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairSmem::kTotal));
     int dev = 0, sms = 0;
     B200_CHECK_CUDA(cudaGetDevice(&dev));
@@ -904,12 +922,19 @@ int launch_pair(const __half* A, long long lda, const __half* B, __half* C, long
         s_max_pairs = n > 0 ? n : 1;
     }
     int pairs = sms / 2 < s_max_pairs ? sms / 2 : s_max_pairs;
-    int per_block = pairs / n_blocks;
-    if (per_block > m_blocks) per_block = m_blocks;
-    if (per_block < 1) per_block = 1;
-    cfg.gridDim = dim3(per_block * n_blocks * 2);
+    int n_ctr = 1;
+    if (RES) {          // pairs bound to column blocks, one ticket counter per block
+        int per_block = pairs / n_blocks;
+        if (per_block > m_blocks) per_block = m_blocks;
+        if (per_block < 1) per_block = 1;
+        pairs = per_block * n_blocks;
+        n_ctr = n_blocks;
+    } else if (pairs > m_blocks * n_blocks) {
+        pairs = m_blocks * n_blocks;
+    }
+    cfg.gridDim = dim3(pairs * 2);
     int* ctr = nullptr;
-    rc = take_counters(n_blocks + 1, stream, &ctr);
+    rc = take_counters(n_ctr + 1, stream, &ctr);
     if (rc) return rc;
     B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, C, ldc, M, N, K, ep, ctr));
     return 0;
@@ -923,8 +948,13 @@ int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, l
                  "gemm_tc: operands must be 16-byte aligned");
     const char* env = getenv("B200_GEMM_WS");
     const bool ws_ok = !(env && env[0] == '0') && K <= WS_KB * BK && M >= 4 * BM;
-    if (ws_ok && pair_enabled() && M >= 64 * BM && N % 256 == 0 && N / 256 <= 64 && ep.act != B200_ACT_SWIGLU)
-        return launch_pair(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+    if (pair_enabled() && M >= 64 * BM && N % 256 == 0) {
+        if (ws_ok && N / 256 <= 64 && ep.act != B200_ACT_SWIGLU)
+            return launch_pair<1>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+        // streaming pairs pay off for long K only (sup, same box: fc2 K = 2048 6.81 -> 6.12 ms per step; qkv / proj / fc1 at
+        // K = 512 measured 4-6 % slower than the single-CTA streaming kernel, whose epilogue they share)
+        if (K >= 1024) return launch_pair<0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+    }
     if (ws_ok && N % 192 == 0 && N / 192 <= 64) return launch_ws<192, 0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     if (ws_ok && N % 128 == 0 && N / 128 <= 64) return launch_ws<128, 0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     if (N % 256 == 0) return launch_tc<256>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);

@@ -190,10 +190,12 @@ def test_lstm_tile_kernel_matches_oracle(native, n, t, reverse):
 
 
 @pytest.mark.parametrize("m,n,k,colblocks,act", [(48 * 431, 1536, 384, True, None), (128 * 70 + 33, 4096, 384, False, "clamp"),
-                                                  (256 * 40, 512, 320, False, "tanh")])
+                                                  (256 * 40, 512, 320, False, "tanh"), (128 * 81 + 5, 1536, 512, False, None),
+                                                  (256 * 33, 512, 2048, False, None)])
 def test_gemm_many_row_blocks(native, m, n, k, colblocks, act):
     """Shapes of the headline batch's GEMMs with enough rows (>= 64 row blocks) for the weight-stationary kernels and, when N
-    is a multiple of 256, the cta_group::2 pair kernel: every output element against fp32 matmul of the same operands."""
+    is a multiple of 256, the cta_group::2 pair kernels (weight-stationary for K <= 384, streaming for K >= 1024, the
+    transformer's fc2): every output element against fp32 matmul of the same operands."""
     g = torch.Generator().manual_seed(m % 1000 + n)
     a = (torch.randn(m, k, generator=g) * 0.5).half()
     w = (torch.randn(n, k, generator=g) / k ** 0.5).half()

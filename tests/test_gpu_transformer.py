@@ -119,7 +119,7 @@ def test_sup_model_call_and_decode():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("m,k,f", [(1000, 512, 2048), (77, 384, 96), (4096, 512, 256), (2000, 384, 192)])
+@pytest.mark.parametrize("m,k,f", [(1000, 512, 2048), (77, 384, 96), (4096, 512, 256), (2000, 384, 192), (256 * 35 + 60, 512, 1024)])
 def test_gemm_with_fused_swiglu(native, m, k, f):
     """B200_ACT_SWIGLU: fc1 with rows interleaved in [32 y | 32 gate] groups == GatedMlp's fc1 -> chunk -> swiglu."""
     from bonito_b200.engine_tf import _interleave_swiglu
