@@ -121,7 +121,7 @@ int b200_gemm_fwd_ex(const void* a, long long lda, const void* b, const void* bi
         return launch_gemm_mma((const __half*)a, lda, (const __half*)b, (__half*)c, ldc, m, n, k, ep,
                                (cudaStream_t)stream);
     return launch_gemm_tc((const __half*)a, lda, (const __half*)b, (__half*)c, ldc, m, n, k, ep, max_ctas,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, impl == B200_GEMM_TCGEN05_PAIR);
 }
 
 int b200_conv_first_fwd(const void* x, int n, int l, int c, int k, const void* w, const void* bias, int act, void* out,

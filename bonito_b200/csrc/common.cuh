@@ -145,4 +145,4 @@ int copy_gemm_profile(long long* host_out);
 int launch_gemm_mma(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
                     const GemmEpilogue& ep, cudaStream_t stream);
 int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
-                   const GemmEpilogue& ep, int max_ctas, cudaStream_t stream);
+                   const GemmEpilogue& ep, int max_ctas, cudaStream_t stream, bool force_pair = false);

@@ -361,7 +361,7 @@ static int gemm_debug() {
 // CTA is bound to ONE column block of B, loads it once into shared memory (<= 144 KB) and streams only A tiles through
 // a 3-stage ring: 98 KB of L2 traffic per tile.
 constexpr int WS_KB = 6;             // K <= 384 fp16 (K <= 768 int8: a 128-byte row holds 64 halves or 128 bytes)
-constexpr int PAIR_DEFAULT = 1;      // cta_group::2 pair kernel for N % 256 == 0, K <= 384 (B200_GEMM_PAIR=0: off)
+constexpr int PAIR_DEFAULT = 0;      // cta_group::2 pair kernels: B200_GEMM_PAIR=1 or impl = B200_GEMM_TCGEN05_PAIR (see launch_gemm_tc)
 
 // INT8 variant (I8 = 1; the reference's --quantize path runs koi's int8 LSTM, bonito/crf/model.py:245): A and B are int8 with
 // 128-element (128-byte) K blocks, tcgen05.mma kind::i8 accumulates s32 in tensor memory, the epilogue multiplies by a
@@ -943,18 +943,22 @@ int launch_pair(const __half* A, long long lda, const __half* B, __half* C, long
 }  // namespace
 
 int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
-                   const GemmEpilogue& ep, int max_ctas, cudaStream_t stream) {
+                   const GemmEpilogue& ep, int max_ctas, cudaStream_t stream, bool force_pair) {
     B200_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0,
                  "gemm_tc: operands must be 16-byte aligned");
     const char* env = getenv("B200_GEMM_WS");
     const bool ws_ok = !(env && env[0] == '0') && K <= WS_KB * BK && M >= 4 * BM;
-    if (pair_enabled() && M >= 64 * BM && N % 256 == 0) {
-        if (ws_ok && N / 256 <= 64 && ep.act != B200_ACT_SWIGLU)
+    // cta_group::2 pairs: faster in isolation (input projection 926-966 -> 989 TFLOP/s, N = 4096 head 725-748 -> 875, sup fc2
+    // 6.81 -> 6.12 ms), but NOT the default: with two batches in flight a pair needs both SMs of a TPC free at once, and next
+    // to the other batch's single-CTA kernels the pair kernels were seen to run with a handful of resident pairs for
+    // milliseconds (end-to-end step 39 instead of 17 ms in 2 of 4 runs), while the pipelined step gains nothing from the
+    // faster GEMM (17.3 vs 17.4 ms: it is bound by SM-milliseconds).
+    if ((force_pair || pair_enabled()) && N % 256 == 0 && (force_pair || M >= 64 * BM)) {
+        if (K <= WS_KB * BK && N / 256 <= 64 && ep.act != B200_ACT_SWIGLU)
             return launch_pair<1>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
-        // streaming pairs pay off for long K only (sup, same box: fc2 K = 2048 6.81 -> 6.12 ms per step; qkv / proj / fc1 at
-        // K = 512 measured 4-6 % slower than the single-CTA streaming kernel, whose epilogue they share)
-        if (K >= 1024) return launch_pair<0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
+        if (K >= 1024 || force_pair) return launch_pair<0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     }
+    B200_REQUIRE(!force_pair, "gemm: the pair kernels need N (%d) to be a multiple of 256", N);
     if (ws_ok && N % 192 == 0 && N / 192 <= 64) return launch_ws<192, 0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     if (ws_ok && N % 128 == 0 && N / 128 <= 64) return launch_ws<128, 0>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);
     if (N % 256 == 0) return launch_tc<256>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);

@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbonito_
 _lib = None
 
 ACT_NONE, ACT_SWISH, ACT_TANH, ACT_CLAMP, ACT_SCALE, ACT_SWIGLU = 0, 1, 2, 3, 4, 5
-GEMM_AUTO, GEMM_TCGEN05, GEMM_MMA_SYNC = 0, 1, 2
+GEMM_AUTO, GEMM_TCGEN05, GEMM_MMA_SYNC, GEMM_TCGEN05_PAIR = 0, 1, 2, 3
 
 MAX_LSTM_LAYERS = 8
 

@@ -42,6 +42,7 @@ extern "C" {
 #define B200_GEMM_AUTO 0 /* tcgen05 (product path) unless B200_GEMM_IMPL=mma is set in the environment */
 #define B200_GEMM_TCGEN05 1
 #define B200_GEMM_MMA_SYNC 2 /* legacy tensor path, kept for on-device cross-checks */
+#define B200_GEMM_TCGEN05_PAIR 3 /* cta_group::2 pair kernels (N % 256 == 0): faster alone, not the default next to other kernels */
 
 /* Library version (major*10000 + minor*100 + patch). */
 int b200_version(void);

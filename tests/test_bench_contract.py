@@ -15,7 +15,7 @@ def _last_json_line(path):
 
 
 def test_committed_bench_line_has_the_contract_keys():
-    d = _last_json_line(os.path.join(ROOT, "profiles", "r01_final_bench.json"))
+    d = _last_json_line(os.path.join(ROOT, "profiles", "r02_bench.json"))
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
         assert key in d, key
@@ -32,10 +32,16 @@ def test_committed_bench_line_has_the_contract_keys():
     for key in ("sm_mhz", "sm_max_mhz", "reasons"):
         assert key in d["clocks"], key
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # BASELINE configs 3, 5 and 1 and the --quantize configuration ride on the same line
+    cfg = d["configs"]
+    for key in ("value", "unit", "ms_per_step", "e2e", "roofline", "stage_ms_per_step", "gpu_launches"):
+        assert key in cfg["config3_sup"], key
+    assert len(cfg["config5_sup_sweep"]) == 3 and all(b["value"] > 0 for b in cfg["config5_sup_sweep"])
+    assert cfg["config1_fast_cpu"]["value"] > 0 and cfg["hac_quantize_int8"]["value"] > 0
 
 
 def test_committed_reference_arm_line():
-    d = _last_json_line(os.path.join(ROOT, "profiles", "r01_final_bench_reference_arm.json"))
+    d = _last_json_line(os.path.join(ROOT, "profiles", "r02_bench_reference.json"))
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] and d["unit"] == "samples/s"

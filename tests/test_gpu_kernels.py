@@ -192,25 +192,27 @@ def test_lstm_tile_kernel_matches_oracle(native, n, t, reverse):
 @pytest.mark.parametrize("m,n,k,colblocks,act", [(48 * 431, 1536, 384, True, None), (128 * 70 + 33, 4096, 384, False, "clamp"),
                                                   (256 * 40, 512, 320, False, "tanh"), (128 * 81 + 5, 1536, 512, False, None),
                                                   (256 * 33, 512, 2048, False, None)])
-def test_gemm_many_row_blocks(native, m, n, k, colblocks, act):
+@pytest.mark.parametrize("impl_name", ["auto", "pair"])
+def test_gemm_many_row_blocks(native, impl_name, m, n, k, colblocks, act):
     """Shapes of the headline batch's GEMMs with enough rows (>= 64 row blocks) for the weight-stationary kernels and, when N
-    is a multiple of 256, the cta_group::2 pair kernels (weight-stationary for K <= 384, streaming for K >= 1024, the
-    transformer's fc2): every output element against fp32 matmul of the same operands."""
+    is a multiple of 256, the cta_group::2 pair kernels (impl "pair": weight-stationary for K <= 384, streaming beyond):
+    every output element against fp32 matmul of the same operands."""
     g = torch.Generator().manual_seed(m % 1000 + n)
     a = (torch.randn(m, k, generator=g) * 0.5).half()
     w = (torch.randn(n, k, generator=g) / k ** 0.5).half()
     bias = torch.randn(n, generator=g).half()
     ref = _ref_gemm(a, w, bias, act, -5.0, 5.0)
     act_code = {None: native.ACT_NONE, "clamp": native.ACT_CLAMP, "tanh": native.ACT_TANH}[act]
+    impl = native.GEMM_TCGEN05_PAIR if impl_name == "pair" else native.GEMM_AUTO
     if colblocks:
         tb, cs, cw = 48, 6, 256
         out = torch.full((m // tb, cs, tb, cw), float("nan"), dtype=torch.float16, device="cuda")
         native.gemm(_dev(a), k, _dev(w), _dev(bias), out, cw, m, n, k, act=act_code, rows_inner=tb, valid_inner=tb, stride_inner=1,
-                    stride_outer=cs * tb, cb_width=cw, cb_rows=tb)
+                    stride_outer=cs * tb, cb_width=cw, cb_rows=tb, impl=impl)
         got = out.float().cpu().permute(0, 2, 1, 3).reshape(m, n)
     else:
         out = torch.full((m, n), float("nan"), dtype=torch.float16, device="cuda")
-        native.gemm(_dev(a), k, _dev(w), _dev(bias), out, n, m, n, k, act=act_code, lo=-5.0, hi=5.0)
+        native.gemm(_dev(a), k, _dev(w), _dev(bias), out, n, m, n, k, act=act_code, lo=-5.0, hi=5.0, impl=impl)
         got = out.float().cpu()
     assert not torch.isnan(got).any()
     err = (got - ref).abs()

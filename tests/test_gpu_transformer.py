@@ -127,7 +127,9 @@ def test_gemm_with_fused_swiglu(native, m, k, f):
     x = torch.randn(m, k, generator=g).half()
     w1 = (torch.randn(2 * f, k, generator=g) / k ** 0.5 * 2).half()
     out = torch.full((m, f), float("nan"), dtype=torch.float16, device="cuda")
-    native.gemm(_dev(x), k, _dev(_interleave_swiglu(w1)), None, out, f, m, 2 * f, k, act=native.ACT_SWIGLU)
+    # the largest case also goes through the streaming cta_group::2 pair kernel
+    impl = native.GEMM_TCGEN05_PAIR if (m >= 8192 and (2 * f) % 256 == 0) else native.GEMM_AUTO
+    native.gemm(_dev(x), k, _dev(_interleave_swiglu(w1)), None, out, f, m, 2 * f, k, act=native.ACT_SWIGLU, impl=impl)
     h = (x.float() @ w1.float().t()).half().float()
     y, gate = h.chunk(2, dim=-1)
     ref = (gate * y / (1 + torch.exp(-gate))).half().float()
