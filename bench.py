@@ -187,7 +187,9 @@ def time_resident(ctx, step, steps, warmup, sampler=None, slots=1):
     batches overlap on the device; the timed region still contains exactly K complete steps.
     """
     main = torch.cuda.current_stream()
-    streams = [torch.cuda.Stream(device=ctx.device) for _ in range(slots)] if slots > 1 else [main]
+    from bonito_b200 import native
+    # streams of their own (torch.cuda.Stream() hands out 32 pooled streams round-robin: two of them may be the same stream)
+    streams = [native.new_stream(ctx.device) for _ in range(slots)] if slots > 1 else [main]
 
     def run(i, events):
         if slots == 1:

@@ -10,6 +10,7 @@ change results: the fp16 cast happens into a pinned buffer and the copy is async
 import numpy as np
 import torch
 
+from bonito_b200 import native
 from bonito_b200.decode import beam_search, to_str
 from bonito_b200.multiprocessing import thread_iter
 from bonito_b200.util import chunk, stitch, batchify, unbatchify
@@ -58,14 +59,33 @@ def compute_scores(model, batch, beam_width=32, beam_cut=100.0, scale=1.0, offse
         return {"moves": moves, "qstring": qstring, "sequence": sequence}
 
 
+_STREAMS = {}
+
+
+def _own_stream(device, role):
+    """One CUDA stream per (device, role) for the life of the process, created through the library (`native.new_stream`):
+    the batches in flight and the copy engine need streams that are really distinct, which pooled torch streams are not."""
+    key = (torch.device(device).index or 0, role)
+    if key not in _STREAMS:
+        _STREAMS[key] = native.new_stream(device)
+    return _STREAMS[key]
+
+
+class _Stage:
+    """Pinned fp16 staging of one input batch and the event of the H2D copy that last read it."""
+
+    def __init__(self, shape):
+        self.buf = torch.empty(shape, dtype=torch.float16, pin_memory=True)
+        self.copied = None
+
+
 class _Slot:
-    """Staging of one in-flight batch: pinned fp16 input, device input, device + pinned result arrays, two events, and the
-    CUDA stream the batch's kernels are enqueued on (one per slot: consecutive batches overlap on the device)."""
+    """One in-flight batch on the device: device input, device + pinned result arrays, two events, and the CUDA stream the
+    batch's kernels are enqueued on (one per slot: consecutive batches overlap on the device)."""
 
     def __init__(self, shape, device, index=0):
         self.index = index
-        self.stream = torch.cuda.Stream(device=device)
-        self.pinned_in = torch.empty(shape, dtype=torch.float16, pin_memory=True)
+        self.stream = _own_stream(device, "slot%d" % index)
         self.dev_in = torch.empty(shape, dtype=torch.float16, device=device)
         self.dev_out = self.pinned_out = None          # uint8 [3, N, T] (moves, sequence, qstring), sized on first use
         self.in_ready, self.done = torch.cuda.Event(), torch.cuda.Event()
@@ -88,7 +108,7 @@ def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=
     if device.type != "cuda":
         raise RuntimeError("bonito_b200 needs a CUDA device (there is no CPU path)")
     rings, pending = {}, []          # input shape -> [slots, next]; FIFO of slots whose results are not handed out yet
-    copy_stream = torch.cuda.Stream(device=device)
+    copy_stream = _own_stream(device, "copy")
     # several batches in flight need one buffer set of the native plan per slot; plans without slots (the generic-layout
     # LSTM path of the narrow models) run their batches back to back on the slots' streams
     multi_slot = _supports_slots(model, device)
@@ -98,13 +118,13 @@ def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=
         moves, sequence, qstring = slot.pinned_out.clone().unbind(0)    # the pinned buffer is reused `depth` batches later
         return slot.key, {"moves": moves, "qstring": qstring, "sequence": sequence}
 
-    def enqueue(slot, key, batch):
+    def enqueue(slot, key, stage):
         with torch.inference_mode(), torch.cuda.device(device):
             slot.key = key
-            slot.pinned_in.copy_(batch)              # fp32 -> fp16 on the host, as the reference does
             with torch.cuda.stream(copy_stream):
-                slot.dev_in.copy_(slot.pinned_in, non_blocking=True)
+                slot.dev_in.copy_(stage.buf, non_blocking=True)
                 slot.in_ready.record(copy_stream)
+                stage.copied = slot.in_ready
             with torch.cuda.stream(slot.stream):
                 main = slot.stream
                 main.wait_event(slot.in_ready)
@@ -128,7 +148,9 @@ def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=
                 while pending:
                     yield result_of(pending.pop(0))
                 rings.clear()
-            rings[shape] = [[_Slot(shape, device, index=i) for i in range(depth)], 0]
+            # depth device slots, depth + 1 pinned input buffers: the host converts and stages batch k + depth while `depth`
+            # batches are on the device, instead of starting on it only when a slot has drained
+            rings[shape] = [[_Slot(shape, device, index=i) for i in range(depth)], 0, [_Stage(shape) for _ in range(depth + 1)], 0]
             if not multi_slot:                       # one shared stream: the batches serialise on the device
                 for sl in rings[shape][0][1:]:
                     sl.stream = rings[shape][0][0].stream
@@ -139,11 +161,16 @@ def score_batches(model, batches, depth=2, beam_width=32, beam_cut=100.0, scale=
                 for sl in rings[shape][0]:
                     sl.stream.wait_stream(torch.cuda.current_stream())
         ring = rings[shape]
+        stage = ring[2][ring[3]]
+        ring[3] = (ring[3] + 1) % (depth + 1)
+        if stage.copied is not None:                 # its last H2D copy (depth + 1 batches ago) has long completed
+            stage.copied.synchronize()
+        stage.buf.copy_(batch)                       # fp32 -> fp16 on the host, as the reference does (batch.half())
         slot = ring[0][ring[1]]
         ring[1] = (ring[1] + 1) % depth
         while any(p is slot for p in pending):       # the slot's previous batch is handed out before the slot is reused
             yield result_of(pending.pop(0))
-        enqueue(slot, key, batch)
+        enqueue(slot, key, stage)
         pending.append(slot)
     while pending:
         yield result_of(pending.pop(0))

@@ -243,6 +243,14 @@ int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank
                              (uint8_t*)moves, (uint8_t*)sequence, (uint8_t*)qstring, (cudaStream_t)stream);
 }
 
+int b200_stream_create(void** stream_out) {
+    B200_REQUIRE(stream_out != nullptr, "stream_create: null pointer argument");
+    cudaStream_t st = nullptr;
+    B200_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *stream_out = (void*)st;
+    return 0;
+}
+
 int b200_quantize_i8(const void* x, void* out, long long n, float scale, void* stream) {
     B200_REQUIRE(x && out && n >= 0, "quantize_i8: bad arguments");
     return launch_quantize_i8((const __half*)x, (int8_t*)out, n, scale, (cudaStream_t)stream);

@@ -949,10 +949,9 @@ int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, l
     const char* env = getenv("B200_GEMM_WS");
     const bool ws_ok = !(env && env[0] == '0') && K <= WS_KB * BK && M >= 4 * BM;
     // cta_group::2 pairs: faster in isolation (input projection 926-966 -> 989 TFLOP/s, N = 4096 head 725-748 -> 875, sup fc2
-    // 6.81 -> 6.12 ms), but NOT the default: with two batches in flight a pair needs both SMs of a TPC free at once, and next
-    // to the other batch's single-CTA kernels the pair kernels were seen to run with a handful of resident pairs for
-    // milliseconds (end-to-end step 39 instead of 17 ms in 2 of 4 runs), while the pipelined step gains nothing from the
-    // faster GEMM (17.3 vs 17.4 ms: it is bound by SM-milliseconds).
+    // 6.81 -> 6.12 ms), but not the default: the pipelined step gains nothing from the faster GEMM (17.3 vs 17.4 ms: it is
+    // bound by SM-milliseconds), and a pair needs both SMs of a TPC free at once while the other batch's
+    // single-CTA kernels come and go.
     if ((force_pair || pair_enabled()) && N % 256 == 0 && (force_pair || M >= 64 * BM)) {
         if (K <= WS_KB * BK && N / 256 <= 64 && ep.act != B200_ACT_SWIGLU)
             return launch_pair<1>(A, lda, B, C, ldc, M, N, K, ep, max_ctas, stream);

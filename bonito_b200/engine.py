@@ -243,8 +243,7 @@ class LstmCrfPlan:
                 ya=torch.empty(nt, T, self.TILE, H, dtype=f16, device=dev),
                 yb=torch.empty(nt, T, self.TILE, H, dtype=f16, device=dev),
                 gx=torch.empty(nt, T, self.TILE, 4 * H, dtype=f16, device=dev),
-                streams=[torch.cuda.Stream(device=dev) for _ in range(nt)],
-                rec_streams=[torch.cuda.Stream(device=dev, priority=-1) for _ in range(nt)],   # high priority
+                streams=_LazyStreams(dev, nt), rec_streams=_LazyStreams(dev, nt),
                 rec_ready=[torch.cuda.Event() for _ in range(nt)], rec_done=[torch.cuda.Event() for _ in range(nt)],
                 done=[torch.cuda.Event() for _ in range(nt)],
                 head=[torch.cuda.Event() for _ in range(nt)],
@@ -380,8 +379,7 @@ class LstmCrfPlan:
                 yq=torch.empty(nt * T * TB * H, dtype=torch.int8, device=dev) if self.quantize else None,
                 # staging of the recurrent kernel's h all-gather: one region per tile (tiles run concurrently)
                 hx=torch.empty(nt, native.lstm_rec_tile_workspace_bytes(TB), dtype=torch.uint8, device=dev),
-                streams=[torch.cuda.Stream(device=dev) for _ in range(nt)],
-                rec_streams=[torch.cuda.Stream(device=dev, priority=-1) for _ in range(nt)],   # high priority
+                streams=_LazyStreams(dev, nt), rec_streams=_LazyStreams(dev, nt),
                 rec_ready=[torch.cuda.Event() for _ in range(nt)], rec_done=[torch.cuda.Event() for _ in range(nt)],
                 done=[torch.cuda.Event() for _ in range(nt)],
                 start=torch.cuda.Event(),
@@ -643,6 +641,25 @@ class _DecodeCache:
 
 
 DECODE_CACHE = _DecodeCache()
+
+
+class _LazyStreams:
+    """Per-tile streams of the tile-pipelined schedules, created on first use with `native.new_stream` (CUDA streams of their
+    own).  `torch.cuda.Stream()` hands out streams from a pool of 32 per device round-robin: the 22 per-tile streams of two buffer
+    sets, created eagerly, pushed later requests (the slot and copy streams of `score_batches`) onto pool entries already in use
+    -- two "different" streams were then one CUDA stream and batches meant to overlap ran back to back (end-to-end step 17 ->
+    20-58 ms, depending on how many streams the process had created before)."""
+
+    def __init__(self, device, n):
+        self.device, self.items = device, [None] * n
+
+    def __getitem__(self, i):
+        if self.items[i] is None:
+            self.items[i] = native.new_stream(self.device)
+        return self.items[i]
+
+    def __len__(self):
+        return len(self.items)
 
 
 def compile_lstm_crf(encoder, device, quantize=False):

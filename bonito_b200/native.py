@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_quantize_i8": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_void_p]),
+    "b200_stream_create": (c_int, [c_void_p]),
     "b200_gemm_i8_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_longlong, c_int, c_int,
                                  c_int, c_void_p]),
@@ -317,6 +318,17 @@ def lstm_crf_fwd(plan_struct, x, scores, stream=None):
         rc = lib.b200_lstm_crf_fwd(ctypes.byref(plan_struct), _ptr(_f16(x, "x")), _ptr(scores), _stream(stream))
     _check(rc, "b200_lstm_crf_fwd")
     return scores
+
+
+def new_stream(device):
+    """A CUDA stream of its own (cudaStreamCreateWithFlags, non-blocking) wrapped for torch.  torch.cuda.Stream() returns
+    one of 32 pooled streams per device round-robin, so streams that must run concurrently can silently be the same stream."""
+    lib = require()
+    handle = c_void_p()
+    with torch.cuda.device(device):
+        rc = lib.b200_stream_create(ctypes.byref(handle))
+    _check(rc, "b200_stream_create")
+    return torch.cuda.ExternalStream(handle.value, device=device)
 
 
 def quantize_i8(x, out, scale=127.0, stream=None):

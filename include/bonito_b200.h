@@ -213,6 +213,13 @@ int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank
                     void* workspace, void* moves, void* sequence, void* qstring, void* stream);
 
 /*
+ * b200_stream_create: a non-blocking CUDA stream on the current device, for the lifetime of the process (host frameworks
+ * that hand out pooled streams -- torch: 32 per device, round-robin -- cannot promise that two streams are distinct; the
+ * pipelined host loop needs its per-batch and copy streams to be).
+ */
+int b200_stream_create(void** stream_out);
+
+/*
  * ---- INT8 input projection (--quantize; reference: koi's int8 LSTM path, bonito/crf/model.py:245, cli/basecaller.py:186-189) ----
  * b200_quantize_i8: out[i] = clamp(rint(x[i] * scale), -127, 127), fp16 -> int8, n a multiple of 8.
  * b200_gemm_i8_fwd: C = act(col_scale[j] * sum_k A_i8[i][k] B_i8[j][k] + bias[j]) -- int8 operands (lda in bytes), s32

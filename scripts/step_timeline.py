@@ -13,7 +13,8 @@ SLOTS = int(os.environ.get("TL_SLOTS", "2"))
 model, spec, weights, L = bench.build_hac(dev, 0, 1, batch=N)
 x = synth.squiggle(64, L, seed=100).repeat(N // 64 + 1, 1, 1)[:N].contiguous().to(dev, torch.float16)
 plan = model.native_plan(dev)
-streams = [torch.cuda.Stream(device=dev) for _ in range(SLOTS)]
+from bonito_b200 import native
+streams = [native.new_stream(dev) for _ in range(SLOTS)]
 
 
 def step(i, events):
