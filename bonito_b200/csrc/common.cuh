@@ -68,6 +68,7 @@ __device__ __forceinline__ float apply_act_f16(float v, int act, float lo, float
         case B200_ACT_TANH: return round_f16(tanh_f(v));
         case B200_ACT_CLAMP: return fminf(fmaxf(v, lo), hi);
         case B200_ACT_SCALE: return round_f16(v * lo);
+        case B200_ACT_TANH_SCALE: return round_f16(round_f16(tanh_f(v)) * lo);
         default: return v;
     }
 }

@@ -208,6 +208,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, unsigned char* 
         case B200_ACT_TANH: block(ActC<B200_ACT_TANH>()); break;
         case B200_ACT_CLAMP: block(ActC<B200_ACT_CLAMP>()); break;
         case B200_ACT_SCALE: block(ActC<B200_ACT_SCALE>()); break;
+        case B200_ACT_TANH_SCALE: block(ActC<B200_ACT_TANH_SCALE>()); break;
         default: block(ActC<B200_ACT_NONE>()); break;
     }
 }

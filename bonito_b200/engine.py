@@ -1,5 +1,5 @@
 """
-Plan builder + executor for the LSTM-CRF encoder (fast / hac / LSTM-sup models).
+Plan builder + executor for the LSTM-CRF encoder (the `bonito.crf` fast / hac models; LSTM widths 96, 128, 256, 384).
 
 `compile_lstm_crf(encoder)` walks a `bonito_b200.nn` module tree of the shape the reference's
 configs describe (`/root/reference/bonito/models/configs/dna_r10.4.1@v4.3.toml`,
@@ -8,22 +8,22 @@ configs describe (`/root/reference/bonito/models/configs/dna_r10.4.1@v4.3.toml`,
     Convolution(1->C1,k5) , Convolution(C1->C2,k5) , Convolution(C2->H,kW,stride s)
     Permute([2,0,1]) , LSTM x L (alternating reverse) , LinearCRFEncoder [, Clamp]
 
-and packs the weights into the operand layouts of the sm_100a kernels (include/bonito_b200.h).
-This is the native swap-in the reference performs in `Model.use_koi`
-(`bonito/crf/model.py:240-246`, koi.lstm.update_graph); like koi it returns scores as
-`[N, T, C]` fp16 without the blank column.
+(LinearCRFEncoder: a plain linear head followed by a Clamp layer, as in the v4+ configs, or the old-style head with
+activation = "tanh" and / or a scale and no Clamp; fixed blank_score) and packs the weights into the operand layouts of
+the sm_100a kernels (include/bonito_b200.h).  This is the native swap-in the reference performs in `Model.use_koi`
+(`bonito/crf/model.py:240-246`, koi.lstm.update_graph); like koi it returns scores as `[N, T, C]` fp16 without the blank
+column.  Anything else raises `UnsupportedModel`.
 
-HBM layout per batch (hac, N=512, L=9996): stem output 164 MB channels-last with halo rows;
-two [T,N,H] activation buffers (655 MB each); one [T,N,4H] gate pre-activation buffer
-(2.6 GB); scores [N,T,1024] (1.75 GB).  Buffers are cached per input shape.
+Width 384 (hac), the headline path (`forward_tiles`, DESIGN.md sections 3 and 4): activations tile-major
+`[tile][T][48][H]`, gate pre-activations `[tile][T][6][48][256]`; per layer ONE input GEMM over all tiles and ONE launch
+of the recurrent kernel (one 6-CTA cluster per 48-chunk tile, 11 clusters for 512 chunks), 15 launches per batch, issued by
+one C call (`b200_lstm_crf_fwd`) unless per-kernel events or intermediate activations are asked for.  Buffers are cached
+per (batch, chunk length, slot): `slot` selects one of several independent buffer sets, so that consecutive batches can
+be in flight on different streams (`score_batches`, bench.py).
 
-Tile pipelining.  The recurrent kernel runs one 8-CTA cluster per tile of 32 chunks, and a B200 can hold only 15
-such clusters at once (GPC packing; `b200_debug_lstm_max_clusters`), so a 512-chunk batch launched layer by layer
-needs two waves per layer.  Chunks are independent, so `forward` instead gives every 32-chunk tile its own CUDA
-stream and enqueues conv-GEMM -> 5 x (input GEMM -> recurrent kernel) -> CRF GEMM per tile: tiles drift apart in
-layer, the 15 cluster slots stay full (80 tile-layers in 5.3 instead of 10 rounds) and the GEMMs of one tile run on
-the SMs the clusters leave free while other tiles are inside their recurrences.  Activations are kept tile-major:
-`[tile][T][32][H]`.
+Other widths (`forward_tiled`): the generic `[T][N][4H]` layout and the `mma.sync` recurrent kernel, tiles of 32 chunks
+pipelined on per-tile streams; `B200_LSTM_TILE=0` sends width 384 down this path with the first-generation tcgen05 kernel
+(8-CTA clusters), `B200_TILE_STREAMS=1` gives the tile-layout path per-tile streams as well (the round-1 schedule).
 """
 
 import torch
@@ -177,8 +177,12 @@ class LstmCrfPlan:
 
         # --- linear CRF head (+ clamp) ---------------------------------------------------------
         crf = crfs[0]
-        if crf.activation is not None or crf.scale is not None or crf.permute is not None:
-            raise UnsupportedModel("native LinearCRFEncoder supports activation=None, scale=None, permute=None")
+        if crf.permute is not None:
+            raise UnsupportedModel("native LinearCRFEncoder supports permute=None")
+        crf_act = _act_code(crf.activation)
+        if crf_act not in (native.ACT_NONE, native.ACT_TANH) or ((crf_act != native.ACT_NONE or crf.scale is not None) and clamps):
+            raise UnsupportedModel("native LinearCRFEncoder supports tanh and / or a scale (old-style configs), or a Clamp layer "
+                                   "behind a plain linear head (v4+ configs)")
         if crf.blank_score is None:
             raise UnsupportedModel("native decode needs a fixed blank_score")
         self.n_base, self.state_len, self.blank_score = crf.n_base, crf.state_len, float(crf.blank_score)
@@ -187,8 +191,12 @@ class LstmCrfPlan:
         self.n_scores = self.wl.shape[0]
         if clamps:
             self.act_l, self.lo, self.hi = native.ACT_CLAMP, float(clamps[0].min), float(clamps[0].max)
+        elif crf_act == native.ACT_TANH and crf.scale is not None:     # e.g. the dna_r9.4.1 configs: tanh, scale 5.0
+            self.act_l, self.lo, self.hi = native.ACT_TANH_SCALE, float(crf.scale), 0.0
+        elif crf.scale is not None:
+            self.act_l, self.lo, self.hi = native.ACT_SCALE, float(crf.scale), 0.0
         else:
-            self.act_l, self.lo, self.hi = native.ACT_NONE, 0.0, 0.0
+            self.act_l, self.lo, self.hi = crf_act, 0.0, 0.0
         self._bufs = {}
 
     # ------------------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ import torch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbonito_b200.so")
 _lib = None
 
-ACT_NONE, ACT_SWISH, ACT_TANH, ACT_CLAMP, ACT_SCALE, ACT_SWIGLU = 0, 1, 2, 3, 4, 5
+ACT_NONE, ACT_SWISH, ACT_TANH, ACT_CLAMP, ACT_SCALE, ACT_SWIGLU, ACT_TANH_SCALE = 0, 1, 2, 3, 4, 5, 6
 GEMM_AUTO, GEMM_TCGEN05, GEMM_MMA_SYNC, GEMM_TCGEN05_PAIR = 0, 1, 2, 3
 
 MAX_LSTM_LAYERS = 8

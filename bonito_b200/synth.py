@@ -42,9 +42,15 @@ def model_config(spec, batchnorm=False, batchsize=32, chunksize=3996, overlap=49
     sub.append(dict(type="permute", dims=[2, 0, 1]))
     for i in range(spec["n_lstm"]):
         sub.append(dict(type="lstm", size=spec["hidden"], insize=spec["hidden"], bias=True, reverse=int(spec["reverse"][i])))
-    sub.append(dict(type="linearcrfencoder", insize=spec["hidden"], n_base=4, state_len=spec["state_len"], bias=False,
-                    blank_score=spec["blank_score"]))
-    sub.append(dict(type="clamp", min=spec["clamp"][0], max=spec["clamp"][1]))
+    crf = dict(type="linearcrfencoder", insize=spec["hidden"], n_base=4, state_len=spec["state_len"], bias=False,
+               blank_score=spec["blank_score"])
+    if spec.get("crf_activation") is not None:          # old-style head: tanh + scale instead of a Clamp layer
+        crf["activation"] = spec["crf_activation"]
+    if spec.get("crf_scale") is not None:
+        crf["scale"] = spec["crf_scale"]
+    sub.append(crf)
+    if spec.get("clamp") is not None:
+        sub.append(dict(type="clamp", min=spec["clamp"][0], max=spec["clamp"][1]))
     return {
         "model": {"package": "bonito.crf"},
         "labels": {"labels": ["N", "A", "C", "G", "T"]},

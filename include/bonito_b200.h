@@ -38,6 +38,7 @@ extern "C" {
  * fp16-rounded y / gate, rounded once -- GatedMlp: flash_attn/modules/mlp.py:99-136, flash_attn/ops/activations.py:107-111
  * as used by bonito/transformer/model.py:100-104.  n % 64 == 0, no bias. */
 #define B200_ACT_SWIGLU 5
+#define B200_ACT_TANH_SCALE 6 /* tanh, then multiply by lo: LinearCRFEncoder(activation="tanh", scale=5.0), bonito/nn.py:283-298 */
 
 #define B200_GEMM_AUTO 0 /* tcgen05 (product path) unless B200_GEMM_IMPL=mma is set in the environment */
 #define B200_GEMM_TCGEN05 1

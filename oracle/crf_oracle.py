@@ -69,12 +69,13 @@ def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, reverse, fp16=False):
     return y.flip(0) if reverse else y
 
 
-def linear_crf(x, weight, bias, activation=None, scale=None, blank_score=None, n_base=4, expand_blanks=True):
-    """LinearCRFEncoder.forward (bonito/nn.py:283-298) on x [T, N, H]."""
-    s = F.linear(x, weight, bias)
-    s = _ACT[activation](s)
+def linear_crf(x, weight, bias, activation=None, scale=None, blank_score=None, n_base=4, expand_blanks=True, fp16=False):
+    """LinearCRFEncoder.forward (bonito/nn.py:283-298) on x [T, N, H]; fp16: every op's result is stored as fp16."""
+    s = _r16(F.linear(x, weight, bias), fp16)
+    if activation is not None:
+        s = _r16(_ACT[activation](s), fp16)
     if scale is not None:
-        s = s * scale
+        s = _r16(s * scale, fp16)
     if blank_score is not None and expand_blanks:
         T, N, C = s.shape
         s = F.pad(s.view(T, N, C // n_base, n_base), (1, 0, 0, 0, 0, 0, 0, 0), value=blank_score).view(T, N, -1)
@@ -101,8 +102,8 @@ def lstm_crf_forward(weights, spec, x, expand_blanks=False, return_features=Fals
         h = lstm_layer(h, weights[f"lstm{i}.w_ih"], weights[f"lstm{i}.w_hh"], weights[f"lstm{i}.b_ih"],
                        weights[f"lstm{i}.b_hh"], spec["reverse"][i], fp16)
         feats[f"lstm{i}"] = h
-    s = linear_crf(_r16(h, fp16), weights["crf.weight"], weights.get("crf.bias"), blank_score=spec["blank_score"],
-                   expand_blanks=False)
+    s = linear_crf(_r16(h, fp16), weights["crf.weight"], weights.get("crf.bias"), activation=spec.get("crf_activation"),
+                   scale=spec.get("crf_scale"), blank_score=spec["blank_score"], expand_blanks=False, fp16=fp16)
     s = _r16(s, fp16)
     if expand_blanks:
         T_, N_, C_ = s.shape

@@ -362,3 +362,32 @@ def test_quantized_input_projection_stays_close_to_fp16():
           f"sequence identity mean {sum(ids) / len(ids):.4f} min {min(ids):.4f}")
     assert err.mean().item() <= 0.08 and err.max().item() <= 3.0, (err.mean().item(), err.max().item())
     assert sum(ids) / len(ids) >= 0.95 and min(ids) >= 0.85
+
+
+@pytest.mark.parametrize("name,n,L", [("hac", 6, 1998), ("fast", 5, 1998)])
+def test_old_style_crf_head_tanh_and_scale(name, n, L):
+    """LinearCRFEncoder(activation="tanh", scale=5.0) without a Clamp layer (the dna_r9.4.1-era configs, bonito/nn.py:283-298):
+    the tanh -> fp16 -> x scale -> fp16 epilogue of the CRF GEMM against the oracle with the same rounding points, and the
+    decode of those scores."""
+    from bonito_b200.crf.model import Model
+    from bonito_b200.decode import beam_search
+    spec = dict(synth.model_spec(name), clamp=None, crf_activation="tanh", crf_scale=5.0)
+    weights = synth.make_weights(spec, seed=31)
+    model = Model(synth.model_config(spec))
+    model.load_state_dict(synth.state_dict_from_weights(spec, weights))
+    model.use_koi(batchsize=32, chunksize=L, quantize=False)
+    model = model.half().eval().to("cuda")
+    x = synth.squiggle(n, L, seed=n + 1).half()
+    with torch.inference_mode():
+        scores = model(x.cuda())
+        seqs, _, moves = beam_search(scores)
+    with torch.no_grad():
+        ref = O.lstm_crf_forward(weights, spec, x.float(), fp16=True).permute(1, 0, 2)
+    got = scores.float().cpu()
+    err = (got - ref).abs()
+    print(f"tanh + scale head ({name}): max |err| {err.max().item():.2e} mean {err.mean().item():.2e}, |scores| max {ref.abs().max().item():.2f}")
+    assert got.abs().max().item() <= 5.0 + 1e-6
+    # one fp16 ulp of the pre-activation (2e-3 at |x| in [2, 4)) times the slope of tanh times 5, plus the output rounding
+    assert err.max().item() <= 2.5e-2 and err.mean().item() <= 1.5e-3, (err.max().item(), err.mean().item())
+    _, o_seq, _, _ = O.decode_native(got.numpy(), spec["state_len"], spec["blank_score"])
+    assert [r[r != 0].tobytes() for r in seqs.cpu().numpy()] == [r[r != 0].tobytes() for r in o_seq]     # identical base sequences
