@@ -124,3 +124,26 @@ def test_oracle_matches_reference_on_the_headline_shape(golden_dir):
     np.testing.assert_allclose(s, gold["scores_ntc"], atol=5e-5)
     seq = build_ref.decode(gold["scores_ntc"], spec["state_len"], 2.0)[1]
     assert [r[r != 0].tobytes().decode() for r in seq] == json.loads(str(gold["strings"]))
+
+
+def test_cpu_reference_model_matches_the_reference_fixtures(gold, golden_dir):
+    """`oracle/cpu_reference.py::CpuReferenceModel` -- what bench.py times as `cpu_baseline` and under `--impl reference` --
+    reproduces the scores the reference's own module tree produced (fast fixture with folded BN; hac headline shape) and
+    the reference's decode_batch strings."""
+    from oracle.cpu_reference import CpuReferenceModel
+    spec = dict(synth.model_spec("fast", n_lstm=2), clamp=None)          # the fast fixture's config has no Clamp layer
+    w, _ = _fused_weights(gold, spec)
+    cfg = json.loads(str(gold["config"]))
+    if any(layer.get("type") == "clamp" for layer in cfg["encoder"]["sublayers"]):
+        spec["clamp"] = (-5.0, 5.0)
+    ref = CpuReferenceModel(spec, w)
+    s = ref(torch.from_numpy(gold["x"]))                                   # [T, N, C] without the blank column
+    want = gold["scores"].reshape(s.shape[0], s.shape[1], -1, 5)[..., 1:].reshape(s.shape)
+    np.testing.assert_allclose(s.numpy(), want, atol=2e-5)
+
+    hac, hspec, hweights = _hac_fixture(golden_dir)
+    href = CpuReferenceModel(hspec, hweights)
+    x = torch.from_numpy(hac["x"].astype(np.float32))
+    np.testing.assert_allclose(href(x).permute(1, 0, 2).numpy(), hac["scores_ntc"], atol=5e-5)
+    seq = href.basecall_batch(x)[1]
+    assert [r[r != 0].tobytes().decode() for r in seq] == json.loads(str(hac["strings"]))
