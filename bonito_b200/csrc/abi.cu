@@ -243,6 +243,17 @@ int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank
                              (uint8_t*)moves, (uint8_t*)sequence, (uint8_t*)qstring, (cudaStream_t)stream);
 }
 
+int b200_chunk_count(long long length, int chunksize, int overlap) {
+    if (length <= 0 || chunksize <= 0 || overlap < 0 || overlap >= chunksize) return 0;
+    return chunk_count(length, chunksize, overlap);
+}
+
+int b200_chunk_signal(const void* signal, int signal_is_f32, long long length, int chunksize, int overlap, void* out,
+                      long long row_stride, void* stream) {
+    B200_REQUIRE(signal && out, "chunk_signal: null pointer argument");
+    return launch_chunk_signal(signal, signal_is_f32, length, chunksize, overlap, (__half*)out, row_stride, (cudaStream_t)stream);
+}
+
 int b200_stream_create(void** stream_out) {
     B200_REQUIRE(stream_out != nullptr, "stream_create: null pointer argument");
     cudaStream_t st = nullptr;

@@ -143,6 +143,9 @@ struct GemmEpilogue {
 
 // Host-side launchers (defined in the .cu files, used by abi.cu)
 int copy_gemm_profile(long long* host_out);
+int chunk_count(long long length, int chunksize, int overlap);
+int launch_chunk_signal(const void* signal, int is_f32, long long length, int chunksize, int overlap, __half* out,
+                        long long row_stride, cudaStream_t stream);
 int launch_gemm_mma(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,
                     const GemmEpilogue& ep, cudaStream_t stream);
 int launch_gemm_tc(const __half* A, long long lda, const __half* B, __half* C, long long ldc, int M, int N, int K,

@@ -24,7 +24,46 @@ quantize_i8_kernel(const __half* __restrict__ x, int8_t* __restrict__ out, long 
     reinterpret_cast<uint2*>(out)[i] = o;
 }
 
+// chunk(): overlapping windows of one read, gathered (and converted to fp16) on the device -- the arithmetic of
+// bonito.util.chunk (bonito/util.py:142-161): a read shorter than a chunk is tiled up to the chunk size; otherwise windows of
+// `chunksize` every `chunksize - overlap` samples starting at stub = (length - overlap) % step, preceded by one window over
+// signal[:chunksize] when stub > 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+chunk_kernel(const T* __restrict__ signal, long long length, int chunksize, int step, int stub, __half* __restrict__ out,
+             long long row_stride) {
+    const int c = blockIdx.y;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= chunksize) return;
+    long long src;
+    if (length < chunksize) src = j % length;
+    else if (stub > 0) src = (c == 0 ? 0 : (long long)stub + (long long)(c - 1) * step) + j;
+    else src = (long long)c * step + j;
+    out[(long long)c * row_stride + j] = __float2half_rn((float)signal[src]);
+}
+
 }  // namespace
+
+// number of chunks bonito.util.chunk returns for a read of `length` samples (chunksize > 0)
+int chunk_count(long long length, int chunksize, int overlap) {
+    if (length < chunksize) return 1;
+    const int step = chunksize - overlap;
+    const long long stub = (length - overlap) % step;
+    return (int)((length - stub - chunksize) / step + 1 + (stub > 0 ? 1 : 0));
+}
+
+int launch_chunk_signal(const void* signal, int is_f32, long long length, int chunksize, int overlap, __half* out,
+                        long long row_stride, cudaStream_t stream) {
+    B200_REQUIRE(length > 0 && chunksize > 0 && overlap >= 0 && overlap < chunksize && row_stride >= chunksize,
+                 "chunk_signal: bad geometry (length %lld, chunksize %d, overlap %d)", length, chunksize, overlap);
+    const int n = chunk_count(length, chunksize, overlap), step = chunksize - overlap;
+    const int stub = length < chunksize ? 0 : (int)((length - overlap) % step);
+    const dim3 grid((unsigned)((chunksize + 255) / 256), (unsigned)n);
+    if (is_f32) chunk_kernel<float><<<grid, 256, 0, stream>>>((const float*)signal, length, chunksize, step, stub, out, row_stride);
+    else chunk_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)signal, length, chunksize, step, stub, out, row_stride);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int launch_quantize_i8(const __half* x, int8_t* out, long long n, float scale, cudaStream_t stream) {
     B200_REQUIRE(n % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 8) == 0,

@@ -70,6 +70,8 @@ SIGNATURES = {
     "b200_crf_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_quantize_i8": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_void_p]),
     "b200_stream_create": (c_int, [c_void_p]),
+    "b200_chunk_count": (c_int, [c_longlong, c_int, c_int]),
+    "b200_chunk_signal": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p]),
     "b200_gemm_i8_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_int, c_float, c_float, c_int, c_int, c_longlong, c_longlong, c_int, c_longlong, c_int, c_int,
                                  c_int, c_void_p]),
@@ -318,6 +320,25 @@ def lstm_crf_fwd(plan_struct, x, scores, stream=None):
         rc = lib.b200_lstm_crf_fwd(ctypes.byref(plan_struct), _ptr(_f16(x, "x")), _ptr(scores), _stream(stream))
     _check(rc, "b200_lstm_crf_fwd")
     return scores
+
+
+def chunk_signal(signal, chunksize, overlap, out=None, stream=None):
+    """bonito.util.chunk for ONE read already on the device: signal [length] (or [1, length]) fp16 / fp32 ->
+    [n_chunks, 1, chunksize] fp16 from one gather kernel (see b200_chunk_signal)."""
+    lib = require()
+    sig = signal.reshape(-1)
+    if not sig.is_cuda or sig.dtype not in (torch.float16, torch.float32) or not sig.is_contiguous():
+        raise ValueError("chunk_signal: a contiguous float16 / float32 CUDA tensor expected")
+    n = lib.b200_chunk_count(sig.numel(), int(chunksize), int(overlap))
+    if n <= 0:
+        raise ValueError(f"chunk_signal: bad geometry (length {sig.numel()}, chunksize {chunksize}, overlap {overlap})")
+    if out is None:
+        out = torch.empty(n, 1, chunksize, dtype=torch.float16, device=sig.device)
+    with torch.cuda.device(sig.device):
+        rc = lib.b200_chunk_signal(_ptr(sig), int(sig.dtype == torch.float32), sig.numel(), int(chunksize), int(overlap),
+                                   _ptr(out), int(chunksize), _stream(stream))
+    _check(rc, "b200_chunk_signal")
+    return out
 
 
 def new_stream(device):

@@ -111,6 +111,10 @@ def chunk(signal, chunksize, overlap):
     Reads shorter than a chunk are tiled up to `chunksize`; when the windows do
     not tile the read exactly a leading chunk over signal[:chunksize] is added.
     """
+    if signal.is_cuda and chunksize > 0 and signal.numel() == signal.shape[-1] and signal.dtype in (torch.float16, torch.float32):
+        # a read that is already on the device: one native gather (+ fp16 conversion) instead of unfold / cat / half()
+        from bonito_b200 import native
+        return native.chunk_signal(signal.contiguous(), chunksize, overlap)
     if signal.ndim == 1:
         signal = signal.unsqueeze(0)
     length = signal.shape[-1]

@@ -214,6 +214,17 @@ int b200_crf_decode(const void* scores, int n, int t, int state_len, float blank
                     void* workspace, void* moves, void* sequence, void* qstring, void* stream);
 
 /*
+ * ---- chunk() on the device (reference: bonito.util.chunk, bonito/util.py:142-161) ----
+ * b200_chunk_count: number of chunks of a read of `length` samples (0 for an invalid geometry).
+ * b200_chunk_signal: signal [length] (fp16, or fp32 when signal_is_f32) -> out [b200_chunk_count][chunksize] fp16, rows
+ *   `row_stride` elements apart: reads shorter than a chunk are tiled, otherwise windows every chunksize - overlap samples from
+ *   stub = (length - overlap) % (chunksize - overlap), preceded by signal[:chunksize] when stub > 0.
+ */
+int b200_chunk_count(long long length, int chunksize, int overlap);
+int b200_chunk_signal(const void* signal, int signal_is_f32, long long length, int chunksize, int overlap, void* out,
+                      long long row_stride, void* stream);
+
+/*
  * b200_stream_create: a non-blocking CUDA stream on the current device, for the lifetime of the process (host frameworks
  * that hand out pooled streams -- torch: 32 per device, round-robin -- cannot promise that two streams are distinct; the
  * pipelined host loop needs its per-batch and copy streams to be).

@@ -55,3 +55,16 @@ def test_pipelined_scoring_refuses_cpu_models():
 
     with pytest.raises(RuntimeError, match="CUDA"):
         list(score_batches(Dummy(), iter([(0, torch.zeros(2, 1, 60))])))
+
+
+def test_chunk_count_is_the_host_functions_chunk_count():
+    """b200_chunk_count (host arithmetic of the device-side chunk()) against bonito_b200.util.chunk, whose windows are pinned
+    by the reference-generated fixture (tests/golden/host_logic.npz)."""
+    import torch
+    from bonito_b200.util import chunk
+    lib = native.load()
+    for length in (1, 37, 499, 500, 3999, 4000, 4001, 7500, 11500, 12000, 40000, 123457):
+        for chunksize, overlap in ((4000, 500), (3996, 498), (9996, 498), (1000, 0), (600, 599)):
+            assert lib.b200_chunk_count(length, chunksize, overlap) == chunk(torch.zeros(length), chunksize, overlap).shape[0], \
+                (length, chunksize, overlap)
+    assert lib.b200_chunk_count(100, 50, 50) == 0 and lib.b200_chunk_count(0, 50, 5) == 0

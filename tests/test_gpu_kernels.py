@@ -246,6 +246,20 @@ def test_gemm_int8_matches_integer_matmul(native, m, n, k, bias, cb):
     assert bool(torch.all(err <= 2e-3 + 1e-3 * ref.abs())), err.max().item()     # one fp16 rounding of the result
 
 
+@pytest.mark.parametrize("length,chunksize,overlap", [(40000, 4000, 500), (12000, 4000, 500), (3996, 3996, 498), (700, 4000, 500),
+                                                      (9996 * 3 + 17, 9996, 498), (4001, 4000, 0)])
+def test_chunk_on_the_device_equals_the_host_function(native, length, chunksize, overlap):
+    """b200_chunk_signal == bonito.util.chunk (pinned by tests/golden/host_logic.npz) followed by .half(), fp32 and fp16 input."""
+    from bonito_b200.util import chunk
+    g = torch.Generator().manual_seed(length)
+    signal = torch.randn(length, generator=g) * 2.0
+    want = chunk(signal, chunksize, overlap).half()
+    got32 = chunk(signal.cuda(), chunksize, overlap)
+    got16 = native.chunk_signal(signal.half().cuda(), chunksize, overlap)
+    assert got32.shape == want.shape and got32.dtype == torch.float16
+    assert torch.equal(got32.cpu(), want) and torch.equal(got16.cpu(), chunk(signal.half(), chunksize, overlap))
+
+
 def test_quantize_i8(native):
     g = torch.Generator().manual_seed(2)
     x = (torch.randn(4096 * 8, generator=g) * 0.6).clamp(-1.5, 1.5).half()
