@@ -52,6 +52,12 @@ def main(args):
     except FileNotFoundError:
         sys.stderr.write(f"> error: failed to load {args.model_directory}\n")
         exit(1)
+    try:
+        # build the native plan now: a layer stack without a B200 kernel is reported here, not from the writer thread
+        model.native_plan()
+    except NotImplementedError as err:          # engine.UnsupportedModel
+        sys.stderr.write(f"> error: no native B200 path for this model (there is no eager fallback): {err}\n")
+        exit(1)
     if args.verbose:
         sys.stderr.write(f"> model basecaller params: {model.config['basecaller']}\n")
 
